@@ -1,0 +1,143 @@
+/* libskd_b200.so -- C ABI of the Blackwell-native structured-distillation step.
+ *
+ * Drop-in boundary for the hot path of irfanICMLL/structure_knowledge_distillation (NetModel.optimize_parameters,
+ * networks/kd_model.py:167-173).  Conventions are the reference's own native-ABI conventions
+ * (libs/src/bn.h:7-19, libs/src/bn.cu:237-300, libs/src/lib_cffi.cpp:36-111):
+ *   - plain pointers and sizes only, fp32 data, no torch types;
+ *   - every function returns 1 on success and 0 on error (the Python side turns 0 into
+ *     RuntimeError("CUDA Error encountered in <fn>"), libs/functions.py:13-16); skd_last_error() gives the text;
+ *   - no allocation, no synchronisation, no hidden state: the caller owns and pre-sizes every buffer (workspaces
+ *     included) and picks the stream; a NULL pointer means "tensor absent" (no affine / gradient not wanted);
+ *   - re-entrant and device-agnostic: work is issued on the caller's current device.
+ * Activation codes: 0 none, 1 leaky_relu(slope), 2 elu, 3 relu.
+ * "NHWC" tensors are [N*H*W rows][C] with an explicit row pitch in floats where noted (channel slices of a concat
+ * buffer are addressed in place).  (sn, sc, sp) are element strides over (image, channel, pixel).
+ */
+#ifndef SKD_B200_H_
+#define SKD_B200_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* skd_last_error(void);
+int skd_version(void);
+
+/* ---- A. InPlace-ABN native ABI: one-for-one replacements of libs/src/bn.h:7-19 ((N, C, S) NCHW views) ---- */
+/* replaces _bn_mean_var_cuda  (bn.h:7,  bn.cu:125-138,237-250): per-channel mean and BIASED variance */
+int skd_bn_mean_var_cuda(int N, int C, int S, const float* x, float* mean, float* var, cudaStream_t);
+/* replaces _bn_forward_cuda   (bn.h:8-9, bn.cu:140-165,252-268): y=(x-mean)*rsqrt(var+eps); z=y*(|w|+eps)+b; y,z may alias x */
+int skd_bn_forward_cuda(int N, int C, int S, const float* x, const float* mean, const float* var, const float* weight,
+                        const float* bias, float* y, float* z, float eps, cudaStream_t);
+/* replaces _bn_edz_eydz_cuda  (bn.h:10-11, bn.cu:167-184,270-283): edz=mean(dz), eydz=mean(y*dz), y recovered from z */
+int skd_bn_edz_eydz_cuda(int N, int C, int S, const float* z, const float* dz, const float* weight, const float* bias,
+                         float* edz, float* eydz, float eps, cudaStream_t);
+/* replaces _bn_backward_cuda  (bn.h:12-14, bn.cu:186-232,285-300): dx; dweight/dbias are += into caller-zeroed buffers */
+int skd_bn_backward_cuda(int N, int C, int S, const float* dz, const float* z, const float* var, const float* weight,
+                         const float* bias, const float* edz, const float* eydz, float* dx, float* dweight, float* dbias,
+                         float eps, cudaStream_t);
+/* replace _leaky_relu_cuda, _leaky_relu_backward_cuda, _elu_cuda, _elu_backward_cuda, _elu_inv_cuda (bn.h:15-19, bn.cu:302-377) */
+int skd_leaky_relu_cuda(int N, float* x, float slope, cudaStream_t);
+int skd_leaky_relu_backward_cuda(int N, const float* x, float* dx, float slope, cudaStream_t);
+int skd_elu_cuda(int N, float* x, cudaStream_t);
+int skd_elu_backward_cuda(int N, const float* x, float* dx, cudaStream_t);
+int skd_elu_inv_cuda(int N, float* x, cudaStream_t);
+
+/* ---- B. fused NHWC ABN used between the tcgen05 convolutions (same math: libs/functions.py:81-109,113-162) ---- */
+int skd_abn_num_splits(long long P, int C);   /* workspace = splits*C*2 floats */
+/* batch stats of x[P][C] -> mean,var (biased); running EMA with n/(n-1) (functions.py:90-91); scale=(|w|+eps)*rsqrt(var+eps),
+   shift=b-mean*scale for the apply pass */
+int skd_abn_stats_nhwc(long long P, int C, const float* x, const float* weight, const float* bias, float eps, float momentum,
+                       float* running_mean, float* running_var, float* mean, float* var, float* scale, float* shift,
+                       float* workspace, int splits, cudaStream_t);
+/* eval-mode / frozen-teacher folding of running statistics into scale/shift */
+int skd_abn_fold(int C, const float* mean, const float* var, const float* weight, const float* bias, float eps, float* scale,
+                 float* shift, cudaStream_t);
+/* out = act(x*scale+shift (+residual)) (*chan_mul[n][c] : Dropout2d mask, S = rows per image); out_pitch in floats;
+   round_tf32: store RNA-rounded TF32 values (the tensor feeds a tensor-core convolution) */
+int skd_abn_apply_nhwc(long long P, int C, int S, const float* x, float* out, int out_pitch, const float* scale,
+                       const float* shift, int act, float slope, const float* residual, const float* chan_mul,
+                       int round_tf32, cudaStream_t);
+/* edz, eydz (means) and dweight=sign(w)*sum(y*dz), dbias=sum(dz) (bn.cu:214-230); dz = dout*chan_mul*act'(out) */
+int skd_abn_bwd_reduce_nhwc(long long P, int C, int S, const float* x, const float* out, const float* dout, const float* mean,
+                            const float* var, const float* weight, float eps, int act, float slope, const float* chan_mul,
+                            float* edz, float* eydz, float* dweight, float* dbias, float* workspace, int splits, cudaStream_t);
+/* dx = (dz - edz - y*eydz)*(|w|+eps)*rsqrt(var+eps); dres = dz (gradient of the residual input), either may be NULL... dx not */
+int skd_abn_bwd_dx_nhwc(long long P, int C, int S, const float* x, const float* out, const float* dout, float* dx, float* dres,
+                        const float* mean, const float* var, const float* weight, const float* edz, const float* eydz,
+                        float eps, int act, float slope, const float* chan_mul, int round_tf32, cudaStream_t);
+
+/* ---- C. losses ---- */
+int skd_loss_max_partials(void);              /* doubles of workspace the reductions below may use (x2 for dsn_ce) */
+/* CriterionPixelWise.forward (utils/criterion.py:219-226): loss = inv_hw * sum_pixels -softmax(T).log_softmax(S) */
+int skd_pixelwise_fwd(int N, int C, int HW, const float* S, long long s_sn, long long s_sc, long long s_sp, const float* T,
+                      long long t_sn, long long t_sc, long long t_sp, float inv_hw, float* loss, double* workspace, cudaStream_t);
+int skd_pixelwise_bwd(int N, int C, int HW, const float* S, long long s_sn, long long s_sc, long long s_sp, const float* T,
+                      long long t_sn, long long t_sc, long long t_sp, float* dS, long long d_sn, long long d_sc, long long d_sp,
+                      const float* grad_out, float inv_hw, cudaStream_t);
+/* CriterionDSN.forward (utils/criterion.py:179-188): w0*CE(up(L0)) + w1*CE(up(L1)), bilinear align_corners to (H,W),
+   ignore_index, mean over valid pixels; L1 may be NULL.  count receives the number of valid pixels. */
+int skd_dsn_ce_fwd(int N, int C, int h, int w, int H, int W, const float* L0, long long a_sn, long long a_sc, long long a_sp,
+                   const float* L1, long long b_sn, long long b_sc, long long b_sp, const long long* labels, int ignore_index,
+                   float w0, float w1, float* loss, float* count, double* workspace, cudaStream_t);
+long long skd_dsn_ce_bwd_workspace_floats(int N, int C, int w, int H, int heads);
+int skd_dsn_ce_bwd(int N, int C, int h, int w, int H, int W, const float* L0, long long a_sn, long long a_sc, long long a_sp,
+                   const float* L1, long long b_sn, long long b_sc, long long b_sp, const long long* labels, int ignore_index,
+                   float w0, float w1, const float* grad_out, const float* count, float* d0, float* d1, float* workspace,
+                   cudaStream_t);
+/* CriterionPairWiseforWholeFeatAfterPool.forward (utils/criterion.py:236-245) + sim_dis_compute (utils/utils.py:170-183):
+   pool: ceil-mode max pool kernel=stride=(ph,pw) -> pooled[N][nodes][C], argmax (pixel index, may be NULL), rnorm[N][nodes] */
+int skd_pairwise_pool(int N, int C, int H, int W, const float* F, long long sn, long long sc, long long sp, int ph, int pw,
+                      float* pooled, int* argmax, float* rnorm, cudaStream_t);
+long long skd_pairwise_gram_partials(int N, int nodes);
+/* E[N][nodes][nodes] = A_T - A_S (may be NULL), loss = sum E^2 / nodes^2 / N */
+int skd_pairwise_gram(int N, int nodes, int CS, int CT, const float* pooled_S, const float* pooled_T, const float* rnorm_S,
+                      const float* rnorm_T, float* E, float* loss, double* workspace, cudaStream_t);
+/* dpooled_S, then scattered through argmax into the pre-zeroed feature gradient dF */
+int skd_pairwise_bwd(int N, int nodes, int CS, const float* E, const float* pooled_S, const float* rnorm_S, const int* argmax,
+                     const float* grad_out, float* dpooled, float* dF, long long sn, long long sc, long long sp, cudaStream_t);
+
+/* ---- D. convolutions (every nn.Conv2d of networks/pspnet_combine.py; cuDNN in the reference) ---- */
+/* tcgen05 implicit GEMM: y = act((conv(x,w))*scale + shift + residual); w is [Cout][KH][KW][Cin]; Cin % 4 == 0 */
+int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                         int ldx, const float* w, float* y, int ldy, const float* scale, const float* shift,
+                         const float* residual, int ldr, int act, float slope, int round_tf32, cudaStream_t);
+/* tcgen05 weight gradient: dw[Cout][KH][KW][Cin] = sum_pixels dy[p][co] * x[p+tap][ci]; workspace from the size query */
+long long skd_conv2d_wgrad_sm100_workspace_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil);
+int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                           int ldx, const float* dy, int ldy, float* dw, float* workspace, cudaStream_t);
+/* SIMT direct forms (3-channel stem, strided dgrad, cross-checks) */
+int skd_conv2d_fwd_direct(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                          int ldx, const float* w, float* y, int ldy, const float* scale, const float* shift, int act,
+                          float slope, cudaStream_t);
+int skd_conv2d_dgrad_direct(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                            const float* dy, int ldy, const float* w, float* dx, int ldx, cudaStream_t);
+int skd_conv2d_wgrad_direct(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                            int ldx, const float* dy, int ldy, float* dw, cudaStream_t);
+int skd_colsum(long long P, int C, const float* dy, int ldy, float* db, cudaStream_t);
+/* wt[Cin][KH][KW][Cout] = w[Cout][KH-1-kh][KW-1-kw][Cin] (dgrad of a stride-1 conv == forward conv with wt, pad' = d*(K-1)-pad) */
+int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w, float* wt, int round_tf32, cudaStream_t);
+int skd_round_tf32(long long n, const float* src, float* dst, cudaStream_t);
+void skd_set_tf32_tma_type(int use_tfloat32_type);
+
+/* ---- E. pooling / resampling / optimiser ---- */
+int skd_pool_out_size_ceil(int in, int k, int s, int p);
+int skd_maxpool3x3s2_fwd(int N, int H, int W, int C, const float* x, float* y, unsigned char* argmax, cudaStream_t);
+int skd_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy, const unsigned char* argmax, float* dx, cudaStream_t);
+int skd_psp_pool_fwd(int N, int H, int W, int C, const float* x, int x_pitch, int levels, const int* sizes, float* pooled, cudaStream_t);
+int skd_psp_pool_bwd(int N, int H, int W, int C, const float* dpooled, int levels, const int* sizes, float* dx, cudaStream_t);
+int skd_psp_upsample_fwd(int N, int H, int W, int C, int s, const float* src, int nbins_total, int first_bin, float* out,
+                         int out_pitch, int chan_off, cudaStream_t);
+int skd_psp_upsample_bwd(int N, int H, int W, int C, int s, const float* dout, int dout_pitch, int chan_off, float* dsrc,
+                         int nbins_total, int first_bin, cudaStream_t);
+int skd_slice_copy(long long rows, int C, const float* src, int src_pitch, int src_off, float* dst, int dst_pitch, int dst_off, cudaStream_t);
+/* G_solver.step (networks/kd_model.py:74,171): v = mu*v + (g*grad_scale + wd*p); p -= lr*v; lr read from device memory */
+int skd_sgd_step(long long n, float* param, const float* grad, float* momentum_buf, const float* lr, float momentum,
+                 float weight_decay, int first_step, float grad_scale, cudaStream_t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKD_B200_H_ */

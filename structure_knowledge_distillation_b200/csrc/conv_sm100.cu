@@ -1,0 +1,318 @@
+// tcgen05 implicit-GEMM 2-D convolution for sm_100a (replaces every cuDNN nn.Conv2d call of
+// networks/pspnet_combine.py on the hot path: forward here; dgrad reuses this kernel on the output gradient with
+// flipped/transposed weights; wgrad is conv_wgrad_sm100.cu).
+//
+//   D[M = N*OH*OW pixels][Cout] = sum_{tap, ci}  X[pixel shifted by tap][ci] * W[Cout][tap][ci]
+//
+// Layout: activations NHWC fp32 (row pitch ld*, so channel slices of a concat buffer are addressable in place),
+// weights [Cout][KH][KW][Cin] (K-major), fp32 storage, TF32 tensor-core math with fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0   TMA producer  : per (tap, 32-channel chunk) one 4-D box {32ch, BW, BH, 1} of X (the tile is a BH x BW
+//                            rectangle of output pixels; the tap shift / padding / stride live in the box coordinates,
+//                            out-of-bounds = hardware zero fill) + one 3-D box {32ch, 1 tap, BLOCK_N} of W, both
+//                            128B-swizzled, landing on a full[] mbarrier of a 4..8-stage ring.
+//   warp 1   MMA issuer    : 4 x tcgen05.mma.kind::tf32 (M=128, N=BLOCK_N, K=8) per stage, accumulator in TMEM
+//                            (2 accumulator stages x BLOCK_N columns), tcgen05.commit releases smem stages / signals
+//                            the epilogue.
+//   warps 2-5 epilogue     : tcgen05.ld 32x32b -> registers -> fused per-channel scale/shift (folded BN or bias),
+//                            residual add, ReLU / leaky-ReLU, optional RNA rounding to TF32 -> 128-bit global stores.
+//                            Overlaps the next tile's MMAs through the second TMEM accumulator stage.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "skd.h"
+#include "sm100_ptx.cuh"
+
+using namespace skd;
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;                 // fp32 elements = 128 B = one swizzle row
+constexpr int kUmmaK = 8;                   // tf32
+constexpr int kThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 4;
+
+struct ConvArgs {
+  int N, OH, OW, Cout, Cin;
+  int KH, KW, stride, pad, dil;
+  int BH, BW, tiles_x, tiles_y;
+  int m_tiles, n_tiles, k_chunks;
+  float* y; int ldy;
+  const float* scale; const float* shift;
+  const float* residual; int ldr;
+  int act; float slope; int round_out;
+  int vec_ok;
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;       // power of two: 64..512
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                      const ConvArgs a) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_w);
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int taps = a.KH * a.KW;
+  const int k_iters = taps * a.k_chunks;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int iy0 = ty * a.BH * a.stride - a.pad, ix0 = tx * a.BW * a.stride - a.pad;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kh = tap / a.KW, kw = tap - kh * a.KW;
+          for (int kc = 0; kc < a.k_chunks; ++kc) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
+            ptx::tma_load_3d(sb, &tmap_w, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      __syncwarp();
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int k = 0; k < k_iters; ++k) {
+        if (lane == 0) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+            const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * kUmmaK * 4, 16, 1024);
+            const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * kUmmaK * 4, 16, 1024);
+            ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs retire
+          if (k == k_iters - 1) ptx::mma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                              // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;                       // accumulator row == pixel inside the tile
+    const int dy = row / a.BW, dx = row - dy * a.BW;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
+      const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+      const int oy = ty * a.BH + dy, ox = tx * a.BW + dx;
+      const bool valid = (oy < a.OH) && (ox < a.OW);
+      const size_t pix = ((size_t)img * a.OH + oy) * a.OW + ox;
+      float* yrow = a.y + pix * a.ldy;
+      const float* rrow = a.residual ? a.residual + pix * a.ldr : nullptr;
+
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + ch * 32, r);
+        ptx::tmem_ld_wait();
+        const int c0 = nt * BLOCK_N + ch * 32;
+        if (valid && c0 < a.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int c = c0 + j + t;
+              float f = __uint_as_float(r[j + t]);
+              if (c < a.Cout) {
+                if (a.scale) f *= __ldg(a.scale + c);
+                if (a.shift) f += __ldg(a.shift + c);
+                if (rrow) f += __ldg(rrow + c);
+                f = act_fwd(f, a.act, a.slope);
+                if (a.round_out) f = ptx::round_tf32(f);
+              }
+              v[t] = f;
+            }
+            const int c = c0 + j;
+            if (a.vec_ok && c + 3 < a.Cout) {
+              *reinterpret_cast<float4*>(yrow + c) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) if (c + t < a.Cout) yrow[c + t] = v[t];
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<C::kTmemCols>(tmem_base); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+
+bool encode(CUtensorMap* m, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+            const cuuint32_t* box, const cuuint32_t* estr, const char* who) {
+  EncodeTiledFn fn = get_encode_tiled();
+  if (!fn) { set_error_msg(who, "cuTensorMapEncodeTiled unavailable (no CUDA driver)"); return false; }
+  CUresult r = fn(m, g_tf32_tma_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                  const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    set_error_msg(who, buf);
+    return false;
+  }
+  return true;
+}
+
+void pick_rect(int OH, int OW, int stride, int* BH, int* BW) {
+  const int cand[6][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {32, 4}, {1, 128}};
+  long long best = -1;
+  for (auto& c : cand) {
+    if (c[0] * stride > 256 || c[1] * stride > 256) continue;
+    const long long t = (long long)((OH + c[0] - 1) / c[0]) * ((OW + c[1] - 1) / c[1]);
+    if (best < 0 || t < best) { best = t; *BH = c[0]; *BW = c[1]; }
+  }
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& tx, const CUtensorMap& tw, const ConvArgs& a, cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_sm100_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { set_error("skd_conv2d_fwd_sm100(attr)", e); return 0; }
+    attr = true;
+  }
+  int grid = a.m_tiles * a.n_tiles;
+  if (grid > kNumSMs) grid = kNumSMs;
+  conv_fwd_sm100_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, a);
+  return finish("skd_conv2d_fwd_sm100");
+}
+
+}  // namespace
+
+extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                    const float* x, int ldx, const float* w, float* y, int ldy, const float* scale,
+                                    const float* shift, const float* residual, int ldr, int act, float slope,
+                                    int round_tf32, cudaStream_t st) {
+  const char* who = "skd_conv2d_fwd_sm100";
+  if (Cin % 4 || ldx % 4 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
+    set_error_msg(who, "Cin and the input pitch must be multiples of 4 floats and pointers 16-byte aligned (TMA)");
+    return 0;
+  }
+  const int OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+  if (OH <= 0 || OW <= 0 || N <= 0) return 1;
+  ConvArgs a;
+  a.N = N; a.OH = OH; a.OW = OW; a.Cout = Cout; a.Cin = Cin; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.dil = dil;
+  pick_rect(OH, OW, stride, &a.BH, &a.BW);
+  a.tiles_x = (OW + a.BW - 1) / a.BW; a.tiles_y = (OH + a.BH - 1) / a.BH;
+  a.m_tiles = N * a.tiles_x * a.tiles_y;
+  a.k_chunks = (Cin + kBlockK - 1) / kBlockK;
+  a.y = y; a.ldy = ldy; a.scale = scale; a.shift = shift; a.residual = residual; a.ldr = ldr;
+  a.act = act; a.slope = slope; a.round_out = round_tf32;
+  a.vec_ok = (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) &&
+             (!residual || ((ldr % 4 == 0) && !(reinterpret_cast<uintptr_t>(residual) & 15)));
+  const int bn = Cout > 128 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
+  a.n_tiles = (Cout + bn - 1) / bn;
+
+  CUtensorMap tx, tw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(a.BW * stride), (cuuint32_t)(a.BH * stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    if (!encode(&tx, 4, x, dims, strides, box, estr, who)) return 0;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)(KH * KW), (cuuint64_t)Cout};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)KH * KW * Cin * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)bn};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (!encode(&tw, 3, w, dims, strides, box, estr, who)) return 0;
+  }
+  switch (bn) {
+    case 256: return launch<256>(tx, tw, a, st);
+    case 128: return launch<128>(tx, tw, a, st);
+    case 64: return launch<64>(tx, tw, a, st);
+    default: return launch<32>(tx, tw, a, st);
+  }
+}

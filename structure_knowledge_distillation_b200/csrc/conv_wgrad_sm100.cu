@@ -1,0 +1,303 @@
+// tcgen05 weight-gradient convolution for sm_100a (cuDNN wgrad in the reference, reached through autograd of every
+// nn.Conv2d of the student: networks/kd_model.py:150 G_loss.backward()).
+//
+//   dW[co][tap][ci] = sum_{pixels p} dY[p][co] * X[p shifted by tap][ci]
+//
+// GEMM view: M = Cout (128 per tile), N = Cin (<=256 per tile, one filter tap per tile), K = pixels.  Both operands are
+// read exactly as they lie in HBM (NHWC: channels contiguous), i.e. as MN-major UMMA operands: per pipeline stage a
+// K-block is a BHk x BWk rectangle of 32 pixels; TMA drops 32-channel x 32-pixel boxes (128B-swizzled, 4 KB each) side
+// by side, and 4 tcgen05.mma.kind::tf32 (K=8 pixels each) consume them.  Split-K over pixel blocks gives >= 2 waves of
+// work units; fp32 partials go to a workspace and a deterministic reduction adds them in fixed order.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "skd.h"
+#include "sm100_ptx.cuh"
+
+using namespace skd;
+
+namespace {
+
+constexpr int kBlockM = 128;               // Cout per tile
+constexpr int kKPix = 32;                  // pixels per stage
+constexpr int kChunkBytes = 32 * kKPix * 4;  // one 32-channel x 32-pixel box
+constexpr int kThreads = 192;
+
+struct WgArgs {
+  int N, OH, OW, Cout, Cin, KH, KW, stride, pad, dil;
+  int BHk, BWk, kb_x, kb_y;                // pixel K-blocks per image
+  int m_tiles, n_tiles, taps, splits, kb_total, kb_per_split;
+  float* ws;                               // [splits][Cout][taps*Cin]
+};
+
+template <int BLOCK_N>
+struct WCfg {
+  static constexpr int kABytes = 4 * kChunkBytes;                    // 128 co
+  static constexpr int kBBytes = (BLOCK_N / 32) * kChunkBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgArgs a) {
+  using C = WCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_dy); ptx::prefetch_tmap(&tmap_x);
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int tiles = a.m_tiles * a.taps * a.n_tiles;
+  const int units = tiles * a.splits;
+  const int kb_per_img = a.kb_x * a.kb_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int tile = u / a.splits, split = u - tile * a.splits;
+        const int mt = tile / (a.taps * a.n_tiles), r = tile - mt * (a.taps * a.n_tiles);
+        const int tap = r / a.n_tiles, nt = r - tap * a.n_tiles;
+        const int kh = tap / a.KW, kw = tap - kh * a.KW;
+        const int kb0 = split * a.kb_per_split;
+        const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int img = kb / kb_per_img, q = kb - img * kb_per_img;
+          const int by = q / a.kb_x, bx = q - by * a.kb_x;
+          const int oy0 = by * a.BHk, ox0 = bx * a.BWk;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            ptx::tma_load_4d(sa + c * kChunkBytes, &tmap_dy, &full_bar[stage], mt * kBlockM + c * 32, ox0, oy0, img);
+#pragma unroll
+          for (int c = 0; c < BLOCK_N / 32; ++c)
+            ptx::tma_load_4d(sb + c * kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32,
+                             ox0 * a.stride - a.pad + kw * a.dil, oy0 * a.stride - a.pad + kh * a.dil, img);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, BLOCK_N, 1, 1);     // both operands MN-major
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int tile = u / a.splits, split = u - tile * a.splits;
+      const int kb0 = split * a.kb_per_split;
+      const int nkb = min(a.kb_total, kb0 + a.kb_per_split) - kb0;
+      if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      __syncwarp();
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int k = 0; k < nkb; ++k) {
+        if (lane == 0) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < kKPix / 8; ++kk) {
+            // MN-major SW128: LBO = distance between 32-channel chunks, SBO = distance between 8-pixel groups
+            const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 1024, kChunkBytes, 1024);
+            const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 1024, kChunkBytes, 1024);
+            ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[stage]);
+          if (k == nkb - 1) ptx::mma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const size_t kdim = (size_t)a.taps * a.Cin;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int tile = u / a.splits, split = u - tile * a.splits;
+      const int mt = tile / (a.taps * a.n_tiles), r = tile - mt * (a.taps * a.n_tiles);
+      const int tap = r / a.n_tiles, nt = r - tap * a.n_tiles;
+      const int co = mt * kBlockM + row;
+      float* orow = a.ws + ((size_t)split * a.Cout + co) * kdim + (size_t)tap * a.Cin;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + ch * 32, v);
+        ptx::tmem_ld_wait();
+        const int c0 = nt * BLOCK_N + ch * 32;
+        if (co < a.Cout && c0 < a.Cin) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int c = c0 + j;
+            if (c + 3 < a.Cin) {
+              *reinterpret_cast<float4*>(orow + c) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) if (c + t < a.Cin) orow[c + t] = __uint_as_float(v[j + t]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<C::kTmemCols>(tmem_base); }
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n4, int splits) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(ws)[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = reinterpret_cast<const float4*>(ws)[(long long)s * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(dw)[i] = a;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr; static bool tried = false;
+  if (!tried) {
+    tried = true; void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct Plan { int OH, OW, BHk, BWk, kb_x, kb_y, kb_total, bn, m_tiles, n_tiles, taps, splits, kb_per_split; };
+
+Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil) {
+  Plan p;
+  p.OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1; p.OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+  const int cand[4][2] = {{4, 8}, {2, 16}, {8, 4}, {1, 32}};
+  long long best = -1;
+  for (auto& c : cand) {
+    const long long t = (long long)((p.OH + c[0] - 1) / c[0]) * ((p.OW + c[1] - 1) / c[1]);
+    if (best < 0 || t < best) { best = t; p.BHk = c[0]; p.BWk = c[1]; }
+  }
+  p.kb_x = (p.OW + p.BWk - 1) / p.BWk; p.kb_y = (p.OH + p.BHk - 1) / p.BHk;
+  p.kb_total = N * p.kb_x * p.kb_y;
+  p.bn = Cin > 128 ? 256 : (Cin > 64 ? 128 : (Cin > 32 ? 64 : 32));
+  p.m_tiles = (Cout + kBlockM - 1) / kBlockM; p.n_tiles = (Cin + p.bn - 1) / p.bn; p.taps = KH * KW;
+  const int tiles = p.m_tiles * p.n_tiles * p.taps;
+  int splits = (2 * kNumSMs + tiles - 1) / tiles;
+  int cap = p.kb_total / 16; if (cap < 1) cap = 1;          // at least 16 k-blocks per unit
+  if (splits > cap) splits = cap;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  return p;
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& tdy, const CUtensorMap& tx, const WgArgs& a, int units, cudaStream_t st) {
+  using C = WCfg<BLOCK_N>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_sm100_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { set_error("skd_conv2d_wgrad_sm100(attr)", e); return 0; }
+    attr = true;
+  }
+  const int grid = units < kNumSMs ? units : kNumSMs;
+  conv_wgrad_sm100_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(tdy, tx, a);
+  return finish("skd_conv2d_wgrad_sm100");
+}
+
+}  // namespace
+
+extern "C" long long skd_conv2d_wgrad_sm100_workspace_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                                                             int pad, int dil) {
+  const Plan p = make_plan(N, H, W, Cin, Cout, KH, KW, stride, pad, dil);
+  return (long long)p.splits * Cout * KH * KW * Cin;
+}
+
+extern "C" int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                      const float* x, int ldx, const float* dy, int ldy, float* dw, float* workspace,
+                                      cudaStream_t st) {
+  const char* who = "skd_conv2d_wgrad_sm100";
+  if (Cin % 4 || Cout % 4 || ldx % 4 || ldy % 4 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
+                                                     reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(workspace)) & 15)) {
+    set_error_msg(who, "channel counts / pitches must be multiples of 4 floats and pointers 16-byte aligned (TMA)");
+    return 0;
+  }
+  const Plan p = make_plan(N, H, W, Cin, Cout, KH, KW, stride, pad, dil);
+  if (p.OH <= 0 || p.OW <= 0 || N <= 0) return 1;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error_msg(who, "cuTensorMapEncodeTiled unavailable (no CUDA driver)"); return 0; }
+  const CUtensorMapDataType dt = skd::g_tf32_tma_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMap tdy, tx;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)p.OW * ldy * 4, (cuuint64_t)p.OH * p.OW * ldy * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.BWk, (cuuint32_t)p.BHk, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tdy, dt, 4, const_cast<float*>(dy), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeTiled(dy) failed"); return 0; }
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)(p.BWk * stride), (cuuint32_t)(p.BHk * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = enc(&tx, dt, 4, const_cast<float*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeTiled(x) failed"); return 0; }
+  }
+  WgArgs a;
+  a.N = N; a.OH = p.OH; a.OW = p.OW; a.Cout = Cout; a.Cin = Cin; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.dil = dil;
+  a.BHk = p.BHk; a.BWk = p.BWk; a.kb_x = p.kb_x; a.kb_y = p.kb_y; a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.taps = p.taps;
+  a.splits = p.splits; a.kb_total = p.kb_total; a.kb_per_split = p.kb_per_split;
+  a.ws = p.splits == 1 ? dw : workspace;
+  const int units = p.m_tiles * p.n_tiles * p.taps * p.splits;
+  int ok;
+  switch (p.bn) {
+    case 256: ok = launch<256>(tdy, tx, a, units, st); break;
+    case 128: ok = launch<128>(tdy, tx, a, units, st); break;
+    case 64: ok = launch<64>(tdy, tx, a, units, st); break;
+    default: ok = launch<32>(tdy, tx, a, units, st); break;
+  }
+  if (!ok) return 0;
+  if (p.splits > 1) {
+    const long long n4 = (long long)Cout * KH * KW * Cin / 4;
+    long long b = (n4 + 255) / 256; if (b > kNumSMs * 8) b = kNumSMs * 8; if (b < 1) b = 1;
+    splitk_reduce_kernel<<<(int)b, 256, 0, st>>>(workspace, dw, n4, p.splits);
+  }
+  return finish(who);
+}

@@ -1,0 +1,48 @@
+// Error reporting + small weight-repacking kernels of libskd_b200.so.
+#include <cstring>
+
+#include "common.cuh"
+#include "skd.h"
+#include "sm100_ptx.cuh"
+
+namespace skd {
+static thread_local char g_err[256] = "";
+int g_tf32_tma_type = 1;
+void set_error(const char* where, cudaError_t err) { snprintf(g_err, sizeof g_err, "%s: %s", where, cudaGetErrorString(err)); }
+void set_error_msg(const char* where, const char* msg) { snprintf(g_err, sizeof g_err, "%s: %s", where, msg); }
+}  // namespace skd
+
+using namespace skd;
+
+namespace {
+__global__ void __launch_bounds__(256)
+flip_transpose_kernel(int Cout, int Cin, int KH, int KW, const float* __restrict__ w, float* __restrict__ wt, int rnd) {
+  const long long total = (long long)Cout * KH * KW * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes wt[ci][kh][kw][co]
+    const int co = (int)(i % Cout); long long r = i / Cout;
+    const int kw = (int)(r % KW); r /= KW; const int kh = (int)(r % KH); const int ci = (int)(r / KH);
+    float v = __ldg(w + (((size_t)co * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)) * Cin + ci);
+    wt[i] = rnd ? ptx::round_tf32(v) : v;
+  }
+}
+__global__ void __launch_bounds__(256) round_kernel(long long n, const float* __restrict__ s, float* __restrict__ d) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = ptx::round_tf32(s[i]);
+}
+int blocks_for(long long n) { long long b = (n + 255) / 256; if (b > kNumSMs * 16) b = kNumSMs * 16; if (b < 1) b = 1; return (int)b; }
+}  // namespace
+
+extern "C" const char* skd_last_error(void) { return skd::g_err; }
+extern "C" int skd_version(void) { return 100; }
+extern "C" void skd_set_tf32_tma_type(int use_tfloat32_type) { skd::g_tf32_tma_type = use_tfloat32_type ? 1 : 0; }
+
+extern "C" int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w, float* wt, int round_tf32, cudaStream_t st) {
+  flip_transpose_kernel<<<blocks_for((long long)Cout * Cin * KH * KW), 256, 0, st>>>(Cout, Cin, KH, KW, w, wt, round_tf32);
+  return finish("skd_weight_flip_transpose");
+}
+extern "C" int skd_round_tf32(long long n, const float* src, float* dst, cudaStream_t st) {
+  if (n <= 0) return 1;
+  round_kernel<<<blocks_for(n), 256, 0, st>>>(n, src, dst);
+  return finish("skd_round_tf32");
+}

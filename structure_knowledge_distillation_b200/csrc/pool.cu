@@ -1,0 +1,309 @@
+// NHWC pooling / resampling / optimizer kernels for sm_100a (all HBM- or latency-bound; float4 over channels).
+//   * 3x3 s2 p1 ceil-mode max-pool of the ResNet stem          networks/pspnet_combine.py:130
+//   * AdaptiveAvgPool2d(1/2/3/6) of the PSP module               networks/pspnet_combine.py:103
+//   * bilinear(align_corners) upsampling of the PSP priors, written straight into their channel slice of the
+//     concat buffer (no torch.cat pass)                           networks/pspnet_combine.py:110-111
+//   * momentum-SGD with weight decay over one flat parameter buffer   networks/kd_model.py:74,171
+#include "common.cuh"
+#include "skd.h"
+
+using namespace skd;
+
+namespace {
+
+__host__ __device__ inline int pool_out_ceil(int in, int k, int s, int p) {
+  int o = (in + 2 * p - k + s - 1) / s + 1;
+  if ((o - 1) * s >= in + p) --o;                      // ATen pooling_output_shape, ceil_mode
+  return o;
+}
+
+int ew_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  if (b > kNumSMs * 16) b = kNumSMs * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__device__ __forceinline__ void max4(float4& best, int4& bi, const float4 v, int idx) {
+  if (v.x > best.x || v.x != v.x) { best.x = v.x; bi.x = idx; }
+  if (v.y > best.y || v.y != v.y) { best.y = v.y; bi.y = idx; }
+  if (v.z > best.z || v.z != v.z) { best.z = v.z; bi.z = idx; }
+  if (v.w > best.w || v.w != v.w) { best.w = v.w; bi.w = idx; }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ arg, int N, int H, int W,
+                   int C4, int OH, int OW) {
+  const long long total = (long long)N * OH * OW * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4); long long r = i / C4;
+    const int ox = (int)(r % OW); r /= OW; const int oy = (int)(r % OH); const int n = (int)(r / OH);
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); int4 bi = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        max4(best, bi, __ldg(reinterpret_cast<const float4*>(x) + (((long long)n * H + iy) * W + ix) * C4 + c4), ky * 3 + kx);
+      }
+    }
+    reinterpret_cast<float4*>(y)[i] = best;
+    reinterpret_cast<uchar4*>(arg)[i] = make_uchar4(bi.x, bi.y, bi.z, bi.w);
+  }
+}
+
+// gather form: every input element looks at the <=4 windows that cover it
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ arg, float* __restrict__ dx, int N, int H,
+                   int W, int C4, int OH, int OW) {
+  const long long total = (long long)N * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4); long long r = i / C4;
+    const int ix = (int)(r % W); r /= W; const int iy = (int)(r % H); const int n = (int)(r / H);
+    float4 g = make_float4(0, 0, 0, 0);
+    for (int oy = iy / 2; oy <= (iy + 1) / 2 && oy < OH; ++oy) {
+      const int ky = iy - (oy * 2 - 1);
+      if (ky < 0 || ky > 2) continue;
+      for (int ox = (ix) / 2; ox <= (ix + 1) / 2 && ox < OW; ++ox) {
+        const int kx = ix - (ox * 2 - 1);
+        if (kx < 0 || kx > 2) continue;
+        const long long o = (((long long)n * OH + oy) * OW + ox) * C4 + c4;
+        const uchar4 a = reinterpret_cast<const uchar4*>(arg)[o];
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy) + o);
+        const int k = ky * 3 + kx;
+        if (a.x == k) g.x += d.x;
+        if (a.y == k) g.y += d.y;
+        if (a.z == k) g.z += d.z;
+        if (a.w == k) g.w += d.w;
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = g;
+  }
+}
+
+// ---- PSP pyramid: all bins of all levels in one launch -------------------------------------------------
+struct Pyramid { int levels; int size[4]; int first_bin[5]; };
+
+__device__ __forceinline__ void bin_of(const Pyramid& p, int bin, int& lvl, int& by, int& bx) {
+  lvl = 0;
+  while (lvl + 1 < p.levels && bin >= p.first_bin[lvl + 1]) ++lvl;
+  const int b = bin - p.first_bin[lvl];
+  by = b / p.size[lvl]; bx = b - by * p.size[lvl];
+}
+__device__ __forceinline__ int bin_lo(int i, int in, int s) { return (i * in) / s; }                  // floor
+__device__ __forceinline__ int bin_hi(int i, int in, int s) { return ((i + 1) * in + s - 1) / s; }    // ceil
+
+// pooled[n][bin][c]; block = 64 channel lanes (x4 channels each... scalar here) x 4 pixel lanes
+__global__ void __launch_bounds__(256)
+psp_pool_fwd_kernel(const float* __restrict__ x, int pitch, int C, int H, int W, Pyramid p, float* __restrict__ pooled) {
+  __shared__ float sv[256];
+  const int bin = blockIdx.x, n = blockIdx.y, cx = threadIdx.x & 63, lane = threadIdx.x >> 6, c = blockIdx.z * 64 + cx;
+  int lvl, by, bx; bin_of(p, bin, lvl, by, bx);
+  const int s = p.size[lvl];
+  const int y0 = bin_lo(by, H, s), y1 = bin_hi(by, H, s), x0 = bin_lo(bx, W, s), x1 = bin_hi(bx, W, s);
+  const int ww = x1 - x0, cnt = (y1 - y0) * ww;
+  float a = 0.f;
+  if (c < C) {
+    const float* base = x + (size_t)n * H * W * pitch + c;
+    for (int k = lane; k < cnt; k += 4) a += __ldg(base + ((size_t)(y0 + k / ww) * W + x0 + k % ww) * pitch);
+  }
+  sv[threadIdx.x] = a;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    a += sv[64 + cx] + sv[128 + cx] + sv[192 + cx];
+    pooled[((size_t)n * gridDim.x + bin) * C + c] = a / (float)cnt;
+  }
+}
+
+// dx[n][y][x][c] = sum over bins containing (y,x) of dpooled/area
+__global__ void __launch_bounds__(256)
+psp_pool_bwd_kernel(const float* __restrict__ dpooled, int C4, int H, int W, int N, Pyramid p, int nbins,
+                    float* __restrict__ dx) {
+  const long long total = (long long)N * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4); long long r = i / C4;
+    const int xx = (int)(r % W); r /= W; const int yy = (int)(r % H); const int n = (int)(r / H);
+    float4 g = make_float4(0, 0, 0, 0);
+    for (int l = 0; l < p.levels; ++l) {
+      const int s = p.size[l];
+      for (int by = 0; by < s; ++by) {
+        const int y0 = bin_lo(by, H, s), y1 = bin_hi(by, H, s);
+        if (yy < y0 || yy >= y1) continue;
+        for (int bx = 0; bx < s; ++bx) {
+          const int x0 = bin_lo(bx, W, s), x1 = bin_hi(bx, W, s);
+          if (xx < x0 || xx >= x1) continue;
+          const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+          const float4 d = __ldg(reinterpret_cast<const float4*>(dpooled) + ((size_t)n * nbins + p.first_bin[l] + by * s + bx) * C4 + c4);
+          g.x += d.x * inv; g.y += d.y * inv; g.z += d.z * inv; g.w += d.w * inv;
+        }
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = g;
+  }
+}
+
+struct Lin { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lin lin(int dst, int in, int out) {
+  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  const float src = scale * (float)dst;
+  Lin b; b.i0 = (int)src; if (b.i0 > in - 1) b.i0 = in - 1;
+  b.i1 = b.i0 + (b.i0 < in - 1 ? 1 : 0); b.l1 = src - (float)b.i0; b.l0 = 1.f - b.l1;
+  return b;
+}
+
+// out[n][y][x][coff + c] = bilinear(src[n][s][s][c]), src = stage output [N][nbins_total][C] slice at first_bin
+__global__ void __launch_bounds__(256)
+psp_up_fwd_kernel(const float* __restrict__ src, int C4, int s, int nb_total, int first_bin, float* __restrict__ out,
+                  int out_pitch4, int coff4, int N, int H, int W) {
+  const long long total = (long long)N * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4); long long r = i / C4;
+    const int xx = (int)(r % W); r /= W; const int yy = (int)(r % H); const int n = (int)(r / H);
+    const Lin by = lin(yy, s, H), bx = lin(xx, s, W);
+    const float4* b = reinterpret_cast<const float4*>(src) + ((size_t)n * nb_total + first_bin) * C4 + c4;
+    const float4 v00 = __ldg(b + (size_t)(by.i0 * s + bx.i0) * C4), v01 = __ldg(b + (size_t)(by.i0 * s + bx.i1) * C4);
+    const float4 v10 = __ldg(b + (size_t)(by.i1 * s + bx.i0) * C4), v11 = __ldg(b + (size_t)(by.i1 * s + bx.i1) * C4);
+    float4 o;
+    o.x = by.l0 * (bx.l0 * v00.x + bx.l1 * v01.x) + by.l1 * (bx.l0 * v10.x + bx.l1 * v11.x);
+    o.y = by.l0 * (bx.l0 * v00.y + bx.l1 * v01.y) + by.l1 * (bx.l0 * v10.y + bx.l1 * v11.y);
+    o.z = by.l0 * (bx.l0 * v00.z + bx.l1 * v01.z) + by.l1 * (bx.l0 * v10.z + bx.l1 * v11.z);
+    o.w = by.l0 * (bx.l0 * v00.w + bx.l1 * v01.w) + by.l1 * (bx.l0 * v10.w + bx.l1 * v11.w);
+    reinterpret_cast<float4*>(out)[(((size_t)n * H + yy) * W + xx) * out_pitch4 + coff4 + c4] = o;
+  }
+}
+
+// dsrc[n][first_bin + iy*s+ix][c] = sum_{y,x} wy*wx * dout[n][y][x][coff + c]; block per (bin, n, 64 channels), 4 lanes
+__global__ void __launch_bounds__(256)
+psp_up_bwd_kernel(const float* __restrict__ dout, int pitch, int coff, int C, int s, int nb_total, int first_bin,
+                  float* __restrict__ dsrc, int H, int W) {
+  __shared__ float sv[256];
+  const int bin = blockIdx.x, n = blockIdx.y, cx = threadIdx.x & 63, lane = threadIdx.x >> 6, c = blockIdx.z * 64 + cx;
+  const int iy = bin / s, ix = bin - iy * s;
+  float a = 0.f;
+  if (c < C) {
+    const float* base = dout + (size_t)n * H * W * pitch + coff + c;
+    for (int k = lane; k < H * W; k += 4) {
+      const int yy = k / W, xx = k - yy * W;
+      const Lin by = lin(yy, s, H);
+      float wy = 0.f; if (by.i0 == iy) wy += by.l0; if (by.i1 == iy) wy += by.l1;
+      if (wy == 0.f) continue;
+      const Lin bx = lin(xx, s, W);
+      float wx = 0.f; if (bx.i0 == ix) wx += bx.l0; if (bx.i1 == ix) wx += bx.l1;
+      if (wx == 0.f) continue;
+      a += wy * wx * __ldg(base + (size_t)k * pitch);
+    }
+  }
+  sv[threadIdx.x] = a;
+  __syncthreads();
+  if (lane == 0 && c < C) dsrc[((size_t)n * nb_total + first_bin + bin) * C + c] = a + sv[64 + cx] + sv[128 + cx] + sv[192 + cx];
+}
+
+// strided channel-slice copy: dst[row][doff + c] = src[row][soff + c]
+__global__ void __launch_bounds__(256)
+slice_copy_kernel(const float* __restrict__ src, int spitch4, int soff4, float* __restrict__ dst, int dpitch4, int doff4,
+                  long long rows, int C4) {
+  const long long total = rows * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C4; const int c4 = (int)(i - r * C4);
+    reinterpret_cast<float4*>(dst)[r * dpitch4 + doff4 + c4] = ld_stream(reinterpret_cast<const float4*>(src) + r * spitch4 + soff4 + c4);
+  }
+}
+
+// v = mu*v + (g + wd*p) ; p -= lr*v   (torch.optim.SGD, dampening 0, first step v = g + wd*p)
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, long long n4, long long n,
+           const float* __restrict__ lr_ptr, float momentum, float wd, int first, float gscale) {
+  const float lr = __ldg(lr_ptr);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = ld_stream(reinterpret_cast<const float4*>(g) + i);
+    float4 vv = first ? make_float4(0, 0, 0, 0) : reinterpret_cast<float4*>(v)[i];
+#define UPD(f) { const float d = gg.f * gscale + wd * pp.f; vv.f = first ? d : momentum * vv.f + d; pp.f -= lr * vv.f; }
+    UPD(x) UPD(y) UPD(z) UPD(w)
+#undef UPD
+    reinterpret_cast<float4*>(v)[i] = vv; reinterpret_cast<float4*>(p)[i] = pp;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = g[i] * gscale + wd * p[i];
+    const float nv = first ? d : momentum * v[i] + d;
+    v[i] = nv; p[i] -= lr * nv;
+  }
+}
+
+Pyramid make_pyramid(int levels, const int* sizes) {
+  Pyramid p; p.levels = levels; p.first_bin[0] = 0;
+  for (int i = 0; i < 4; ++i) p.size[i] = i < levels ? sizes[i] : 1;
+  for (int i = 0; i < levels; ++i) p.first_bin[i + 1] = p.first_bin[i] + sizes[i] * sizes[i];
+  return p;
+}
+
+}  // namespace
+
+extern "C" int skd_pool_out_size_ceil(int in, int k, int s, int p) { return pool_out_ceil(in, k, s, p); }
+
+extern "C" int skd_maxpool3x3s2_fwd(int N, int H, int W, int C, const float* x, float* y, unsigned char* argmax,
+                                    cudaStream_t st) {
+  if (C % 4) { set_error_msg("skd_maxpool3x3s2_fwd", "C % 4 != 0"); return 0; }
+  const int OH = pool_out_ceil(H, 3, 2, 1), OW = pool_out_ceil(W, 3, 2, 1);
+  maxpool_fwd_kernel<<<ew_blocks((long long)N * OH * OW * (C / 4)), 256, 0, st>>>(x, y, argmax, N, H, W, C / 4, OH, OW);
+  return finish("skd_maxpool3x3s2_fwd");
+}
+
+extern "C" int skd_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy, const unsigned char* argmax, float* dx,
+                                    cudaStream_t st) {
+  if (C % 4) { set_error_msg("skd_maxpool3x3s2_bwd", "C % 4 != 0"); return 0; }
+  const int OH = pool_out_ceil(H, 3, 2, 1), OW = pool_out_ceil(W, 3, 2, 1);
+  maxpool_bwd_kernel<<<ew_blocks((long long)N * H * W * (C / 4)), 256, 0, st>>>(dy, argmax, dx, N, H, W, C / 4, OH, OW);
+  return finish("skd_maxpool3x3s2_bwd");
+}
+
+extern "C" int skd_psp_pool_fwd(int N, int H, int W, int C, const float* x, int x_pitch, int levels, const int* sizes,
+                                float* pooled, cudaStream_t st) {
+  if (levels < 1 || levels > 4) { set_error_msg("skd_psp_pool_fwd", "1..4 pyramid levels"); return 0; }
+  const Pyramid p = make_pyramid(levels, sizes);
+  psp_pool_fwd_kernel<<<dim3(p.first_bin[levels], N, (C + 63) / 64), 256, 0, st>>>(x, x_pitch, C, H, W, p, pooled);
+  return finish("skd_psp_pool_fwd");
+}
+
+extern "C" int skd_psp_pool_bwd(int N, int H, int W, int C, const float* dpooled, int levels, const int* sizes, float* dx,
+                                cudaStream_t st) {
+  if (C % 4 || levels < 1 || levels > 4) { set_error_msg("skd_psp_pool_bwd", "C % 4 != 0 or bad levels"); return 0; }
+  const Pyramid p = make_pyramid(levels, sizes);
+  psp_pool_bwd_kernel<<<ew_blocks((long long)N * H * W * (C / 4)), 256, 0, st>>>(dpooled, C / 4, H, W, N, p, p.first_bin[levels], dx);
+  return finish("skd_psp_pool_bwd");
+}
+
+extern "C" int skd_psp_upsample_fwd(int N, int H, int W, int C, int s, const float* src, int nbins_total, int first_bin,
+                                    float* out, int out_pitch, int chan_off, cudaStream_t st) {
+  if (C % 4 || out_pitch % 4 || chan_off % 4) { set_error_msg("skd_psp_upsample_fwd", "channel counts must be multiples of 4"); return 0; }
+  psp_up_fwd_kernel<<<ew_blocks((long long)N * H * W * (C / 4)), 256, 0, st>>>(src, C / 4, s, nbins_total, first_bin, out,
+                                                                              out_pitch / 4, chan_off / 4, N, H, W);
+  return finish("skd_psp_upsample_fwd");
+}
+
+extern "C" int skd_psp_upsample_bwd(int N, int H, int W, int C, int s, const float* dout, int dout_pitch, int chan_off,
+                                    float* dsrc, int nbins_total, int first_bin, cudaStream_t st) {
+  psp_up_bwd_kernel<<<dim3(s * s, N, (C + 63) / 64), 256, 0, st>>>(dout, dout_pitch, chan_off, C, s, nbins_total, first_bin,
+                                                                  dsrc, H, W);
+  return finish("skd_psp_upsample_bwd");
+}
+
+extern "C" int skd_slice_copy(long long rows, int C, const float* src, int src_pitch, int src_off, float* dst, int dst_pitch,
+                              int dst_off, cudaStream_t st) {
+  if ((C | src_pitch | src_off | dst_pitch | dst_off) % 4) { set_error_msg("skd_slice_copy", "multiples of 4 channels only"); return 0; }
+  slice_copy_kernel<<<ew_blocks(rows * (C / 4)), 256, 0, st>>>(src, src_pitch / 4, src_off / 4, dst, dst_pitch / 4, dst_off / 4,
+                                                              rows, C / 4);
+  return finish("skd_slice_copy");
+}
+
+extern "C" int skd_sgd_step(long long n, float* param, const float* grad, float* momentum_buf, const float* lr, float momentum,
+                            float weight_decay, int first_step, float grad_scale, cudaStream_t st) {
+  if (n <= 0) return 1;
+  const bool al = !((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(momentum_buf)) & 15);
+  const long long n4 = al ? n / 4 : 0;
+  sgd_kernel<<<ew_blocks(n / 4 + 1), 256, 0, st>>>(param, grad, momentum_buf, n4, n, lr, momentum, weight_decay, first_step, grad_scale);
+  return finish("skd_sgd_step");
+}

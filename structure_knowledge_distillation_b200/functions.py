@@ -1,0 +1,176 @@
+"""torch.autograd.Functions over the sm_100a kernels (the reference's libs/functions.py role, for the whole hot path).
+
+Conventions kept from the reference (libs/functions.py:70-162): ctx.save_for_backward for tensors, non-tensor
+arguments get None gradients, backward is once-differentiable (no double backward through hand-written kernels).
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------ losses
+class PixelWiseLoss(torch.autograd.Function):
+    """CriterionPixelWise math (utils/criterion.py:219-226) in one warp-reduced kernel each way."""
+
+    @staticmethod
+    def forward(ctx, logits_S, logits_T):
+        ctx.save_for_backward(logits_S, logits_T)
+        return ops.pixelwise_fwd(logits_S, logits_T)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        S, T = ctx.saved_tensors
+        return ops.pixelwise_bwd(S, T, g.contiguous()), None
+
+
+class PairWiseLoss(torch.autograd.Function):
+    """CriterionPairWiseforWholeFeatAfterPool math (utils/criterion.py:236-245, utils/utils.py:170-183)."""
+
+    @staticmethod
+    def forward(ctx, feat_S, feat_T, ph, pw):
+        pS, arg, rS = ops.pairwise_pool(feat_S, ph, pw, True)
+        pT, _, rT = ops.pairwise_pool(feat_T, ph, pw, False)
+        loss, E = ops.pairwise_gram(pS, pT, rS, rT, True)
+        ctx.save_for_backward(E, pS, rS, arg, feat_S)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        E, pS, rS, arg, feat_S = ctx.saved_tensors
+        return ops.pairwise_bwd(E, pS, rS, arg, g.contiguous(), feat_S), None, None, None
+
+
+class DsnCrossEntropy(torch.autograd.Function):
+    """CriterionDSN math (utils/criterion.py:179-188): fused upsample + log-softmax + NLL for both heads."""
+
+    @staticmethod
+    def forward(ctx, l0, l1, labels, ignore_index, w0, w1):
+        out = ops.dsn_ce_fwd(l0, l1, labels, ignore_index, w0, w1)
+        ctx.save_for_backward(l0, l1, labels, out)
+        ctx.cfg = (ignore_index, w0, w1)
+        return out[0].clone()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        l0, l1, labels, out = ctx.saved_tensors
+        ig, w0, w1 = ctx.cfg
+        d0, d1 = ops.dsn_ce_bwd(l0, l1, labels, ig, w0, w1, g.contiguous(), out[1])
+        return d0, d1, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ layers
+class Conv2d(torch.autograd.Function):
+    """nn.Conv2d forward / dgrad / wgrad on tcgen05 (SIMT direct kernels for the 3-channel stem and strided dgrad).
+    x is NHWC-stored; weight is the (Cout,Cin,KH,KW) parameter held in channels-last (OHWI) storage."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, dil):
+        w = ops.weight_ohwi(weight)
+        y = ops.conv2d_fwd(x, w, stride, pad, dil, shift=bias)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, pad, dil, bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, pad, dil, has_bias = ctx.cfg
+        dy = ops.to_nhwc(dy)
+        w = ops.weight_ohwi(weight)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv2d_dgrad(dy, w, x.shape, stride, pad, dil)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv2d_wgrad(x, dy, (w.shape[1], w.shape[2]), stride, pad, dil).permute(0, 3, 1, 2)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(dy)
+        return dx, dw, db, None, None, None
+
+
+class ABN(torch.autograd.Function):
+    """InPlaceABN(Sync) forward/backward (libs/functions.py:70-162) fused with what follows it in the network:
+    the ReLU the backbone applies right after an activation='none' ABN (networks/pspnet_combine.py:36,69,177), the
+    residual add + ReLU that closes a block (:42-43,81-82) and the Dropout2d after the PSP / DSN ABN (:99,143)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, activation, slope, residual,
+                chan_mul):
+        if training:
+            st = ops.abn_stats(x, weight, bias, eps, momentum, running_mean, running_var)
+        else:
+            sc, sh = ops.abn_fold(running_mean, running_var, weight, bias, eps)
+            st = torch.stack([running_mean, running_var, sc, sh])
+        out = ops.abn_apply(x, st[2], st[3], activation, slope, residual=residual, chan_mul=chan_mul)
+        ctx.save_for_backward(x, out, st, weight, chan_mul)
+        ctx.cfg = (training, eps, activation, slope, residual is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, out, st, weight, chan_mul = ctx.saved_tensors
+        training, eps, activation, slope, has_res = ctx.cfg
+        if not training:
+            raise NotImplementedError("eval-mode ABN backward is not on the distillation path (teacher runs under no_grad)")
+        dx, dres, dw, db = ops.abn_backward(x, out, ops.to_nhwc(dout), st, weight, eps, activation, slope, chan_mul, has_res)
+        return dx, dw, db, None, None, None, None, None, None, None, dres, None
+
+
+class MaxPool3x3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y, arg = ops.maxpool_fwd(x)
+        ctx.save_for_backward(arg)
+        ctx.shape = x.shape
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        return ops.maxpool_bwd(ops.to_nhwc(dy), arg, ctx.shape)
+
+
+class PspPool(torch.autograd.Function):
+    """AdaptiveAvgPool2d(1/2/3/6) of the PSP module in one launch -> (N, 50, C)."""
+
+    @staticmethod
+    def forward(ctx, x, sizes):
+        ctx.sizes, ctx.shape = sizes, x.shape
+        return ops.psp_pool_fwd(x, list(sizes))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dp):
+        return ops.psp_pool_bwd(dp.contiguous(), list(ctx.sizes), ctx.shape), None
+
+
+class PspAssemble(torch.autograd.Function):
+    """torch.cat([upsample(stage_i)..., feats], 1) written in place into one NHWC buffer (pspnet_combine.py:110-111)."""
+
+    @staticmethod
+    def forward(ctx, feats, sizes, *stages):
+        n, c, h, w = feats.shape
+        cs = stages[0].shape[2]
+        ctot = len(stages) * cs + c
+        buf = ops.empty_nhwc(n, ctot, h, w, feats.device)
+        for i, (s, stg) in enumerate(zip(sizes, stages)):
+            ops.psp_upsample_fwd(stg.contiguous(), s, buf, i * cs)
+        ops.slice_copy(feats, 0, buf, len(stages) * cs, c)
+        ctx.cfg = (sizes, cs, c, feats.shape)
+        return buf
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dbuf):
+        sizes, cs, c, fshape = ctx.cfg
+        dbuf = ops.to_nhwc(dbuf)
+        dfe = ops.empty_nhwc(fshape[0], c, fshape[2], fshape[3], dbuf.device)
+        ops.slice_copy(dbuf, len(sizes) * cs, dfe, 0, c)
+        dst = tuple(ops.psp_upsample_bwd(dbuf, s, cs, i * cs) for i, s in enumerate(sizes))
+        return (dfe, None) + dst

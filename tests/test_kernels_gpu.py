@@ -1,0 +1,326 @@
+"""Kernel-level parity on the B200 (all through the C ABI): every hand-written kernel against
+  * the reference's own native kernels (oracle/_ref/libbn_ref.so = libs/src/bn.cu built for sm_100a) for the ABN ABI,
+  * the CPU oracle (oracle/port.py) / the committed golden fixtures for the losses,
+  * a float64 torch restatement for the convolutions (TF32 tolerance stated per test).
+"""
+import ctypes
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from structure_knowledge_distillation_b200 import ops as o
+    return o
+
+
+@pytest.fixture(scope="module")
+def L():
+    from structure_knowledge_distillation_b200._cabi import lib
+    return lib()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------- ABN, reference ABI
+def _ref_bn():
+    path = os.path.join(ROOT, "oracle", "_ref", "libbn_ref.so")
+    if not os.path.exists(path):
+        return None
+    return ctypes.CDLL(path)
+
+
+ABN_SHAPES = [(2, 5, 7 * 3), (8, 64, 33 * 65), (3, 19, 1001), (1, 128, 4), (4, 256, 65 * 129), (2, 7, 1)]
+
+
+@pytest.mark.parametrize("N,C,S", ABN_SHAPES)
+def test_bn_native_abi_matches_reference_bn_cu(L, N, C, S):
+    """Same raw-pointer calls into our library and into the reference's bn.cu (sm_100a build): <= 1e-5 relative."""
+    ref = _ref_bn()
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + C)
+    x = torch.randn(N, C, S, device="cuda", generator=g) * 2 + 0.5
+    w = torch.randn(C, device="cuda", generator=g); b = torch.randn(C, device="cuda", generator=g)
+    w[0] = -abs(w[0])                                      # exercise the sign-corrected dweight (bn.cu:217-223)
+    dz = torch.randn(N, C, S, device="cuda", generator=g)
+    eps = 1e-5
+    vp = ctypes.c_void_p
+    fl = ctypes.c_float
+
+    def run(lib, pre):
+        mean = torch.empty(C, device="cuda"); var = torch.empty(C, device="cuda")
+        z = x.clone()
+        f = lambda name: getattr(lib, pre + name)
+        assert f("bn_mean_var_cuda")(N, C, S, vp(x.data_ptr()), vp(mean.data_ptr()), vp(var.data_ptr()), vp(_st()))
+        assert f("bn_forward_cuda")(N, C, S, vp(z.data_ptr()), vp(mean.data_ptr()), vp(var.data_ptr()), vp(w.data_ptr()),
+                                    vp(b.data_ptr()), vp(z.data_ptr()), vp(z.data_ptr()), fl(eps), vp(_st()))     # in place
+        edz = torch.empty(C, device="cuda"); eydz = torch.empty(C, device="cuda")
+        assert f("bn_edz_eydz_cuda")(N, C, S, vp(z.data_ptr()), vp(dz.data_ptr()), vp(w.data_ptr()), vp(b.data_ptr()),
+                                     vp(edz.data_ptr()), vp(eydz.data_ptr()), fl(eps), vp(_st()))
+        dx = torch.empty_like(x); dw = torch.zeros(C, device="cuda"); db = torch.zeros(C, device="cuda")
+        assert f("bn_backward_cuda")(N, C, S, vp(dz.data_ptr()), vp(z.data_ptr()), vp(var.data_ptr()), vp(w.data_ptr()),
+                                     vp(b.data_ptr()), vp(edz.data_ptr()), vp(eydz.data_ptr()), vp(dx.data_ptr()),
+                                     vp(dw.data_ptr()), vp(db.data_ptr()), fl(eps), vp(_st()))
+        torch.cuda.synchronize()
+        return dict(mean=mean, var=var, z=z, edz=edz, eydz=eydz, dx=dx, dw=dw, db=db)
+
+    mine = run(L._dll, "skd_")
+    # float64 restatement of bn.cu as the always-available anchor
+    xd = x.double(); m = xd.mean((0, 2)); v = ((xd - m[None, :, None]) ** 2).mean((0, 2))
+    assert rel(mine["mean"], m) < 1e-5 and rel(mine["var"], v) < 2e-5
+    gamma = w.double().abs() + eps
+    zd = (xd - m[None, :, None]) / (v + eps).sqrt()[None, :, None] * gamma[None, :, None] + b.double()[None, :, None]
+    assert rel(mine["z"], zd) < 1e-5
+    if ref is not None:
+        theirs = run(ref, "_")
+        for k in mine:
+            assert rel(mine[k], theirs[k]) < 2e-5, (k, rel(mine[k], theirs[k]))
+
+
+def test_activation_abi(L):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for n in (1, 7, 1024, 4099):
+        x = torch.randn(n, device="cuda", generator=g)
+        y = x.clone()
+        L.skd_leaky_relu_cuda(n, y.data_ptr(), 0.01, _st())
+        assert torch.equal(y, torch.where(x < 0, x * 0.01, x))
+        d = torch.randn(n, device="cuda", generator=g); d0 = d.clone()
+        L.skd_leaky_relu_backward_cuda(n, y.data_ptr(), d.data_ptr(), 0.01, _st())
+        assert torch.equal(d, torch.where(y < 0, d0 * 0.01, d0))
+        L.skd_leaky_relu_cuda(n, y.data_ptr(), 1.0 / 0.01, _st())          # inversion trick (functions.py:56-57)
+        assert torch.allclose(y, x, rtol=1e-6, atol=1e-7)
+        e = x.clone(); L.skd_elu_cuda(n, e.data_ptr(), _st())
+        assert torch.allclose(e, F.elu(x), rtol=1e-6, atol=1e-7)
+        e2 = e.clone(); L.skd_elu_inv_cuda(n, e2.data_ptr(), _st())
+        assert torch.allclose(e2, x, rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- ABN, fused NHWC path
+@pytest.mark.parametrize("N,C,H,W,act,res,drop", [(2, 64, 9, 13, "relu", True, False), (2, 128, 7, 5, "leaky_relu", False, True),
+                                                   (1, 512, 3, 3, "none", False, False), (3, 76, 5, 4, "relu", False, False),
+                                                   (2, 2048, 2, 3, "leaky_relu", False, False)])
+def test_abn_nhwc_fwd_bwd_vs_oracle(ops, N, C, H, W, act, res, drop):
+    from oracle import port
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(N, C, H, W, generator=g) * 1.5 + 0.3
+    w = torch.randn(C, generator=g); b = torch.randn(C, generator=g) * 0.2
+    r = torch.randn(N, C, H, W, generator=g) if res else None
+    mask = (torch.rand(N, C, generator=g) > 0.3).float() / 0.7 if drop else None
+    dout = torch.randn(N, C, H, W, generator=g)
+    eps, slope = 1e-5, 0.01
+    # oracle (CPU, autograd through the reference-faithful ABN Function)
+    xo = x.clone().requires_grad_(True); wo = w.clone().requires_grad_(True); bo = b.clone().requires_grad_(True)
+    ro = r.clone().requires_grad_(True) if res else None
+    rm, rv = torch.zeros(C), torch.ones(C)
+    core_act = "none" if act == "relu" else act
+    z = port._ABNFn.apply(xo, wo, bo, rm, rv, True, 0.1, eps, core_act, slope)
+    if res: z = z + ro
+    if act == "relu": z = torch.relu(z)
+    if drop: z = z * mask[:, :, None, None]
+    z.backward(dout)
+    # ours
+    dev = "cuda"
+    xc = ops.to_nhwc(x.to(dev)); wc, bc = w.to(dev), b.to(dev)
+    rmc, rvc = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    st = ops.abn_stats(xc, wc, bc, eps, 0.1, rmc, rvc)
+    out = ops.abn_apply(xc, st[2], st[3], act, slope, residual=ops.to_nhwc(r.to(dev)) if res else None,
+                        chan_mul=mask.to(dev) if drop else None)
+    assert rel(out.cpu(), z.detach()) < 1e-5
+    assert rel(rmc.cpu(), rm) < 1e-5 and rel(rvc.cpu(), rv) < 1e-5
+    dx, dres, dw, db = ops.abn_backward(xc, out, ops.to_nhwc(dout.to(dev)), st, wc, eps, act, slope,
+                                        mask.to(dev) if drop else None, res)
+    assert rel(dx.cpu(), xo.grad) < 2e-4
+    assert rel(dw.cpu(), wo.grad) < 2e-4 and rel(db.cpu(), bo.grad) < 2e-4
+    if res:
+        assert rel(dres.cpu(), ro.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- losses vs golden
+def _golden(name):
+    return torch.load(os.path.join(ROOT, "tests", "golden", name), weights_only=False)
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_losses_match_reference_goldens(ops, layout):
+    """utils/criterion.py classes, run by oracle/make_golden.py on the real reference: 1e-3 relative is the contract,
+    the kernels are fp32 so we hold 2e-5 on losses and 1e-4 on gradients."""
+    from oracle import cases
+    from structure_knowledge_distillation_b200.utils import criterion as C
+    gold = _golden("criteria.pt")["criterion"]
+    for name, n, cs, ct, h, w, scale, (lh, lw) in cases.CRITERION_CASES:
+        S, T = cases.criterion_inputs(n, cs, ct, 19, h, w, seed=len(name) * 7 + n)
+        g = cases.seeded(5 + n)
+        labels = torch.randint(0, 19, (n, lh, lw), generator=g)
+        labels[torch.rand(n, lh, lw, generator=g) < 0.05] = 255
+        conv = (lambda t: t.cuda()) if layout == "nchw" else (lambda t: t.cuda().contiguous(memory_format=torch.channels_last))
+        Sg = [conv(t).requires_grad_(True) if t is not None else None for t in S]
+        Tg = [conv(t) if t is not None else None for t in T]
+        pi = C.CriterionPixelWise()(Sg, Tg)
+        pa = C.CriterionPairWiseforWholeFeatAfterPool(scale=scale, feat_ind=-5)(Sg, Tg)
+        ce = C.CriterionDSN()(Sg, labels.cuda())
+        G = gold[name]
+        assert abs(float(pi) - float(G["pi"])) / abs(float(G["pi"])) < 2e-5, (name, float(pi), float(G["pi"]))
+        assert abs(float(pa) - float(G["pa"])) / abs(float(G["pa"])) < 5e-5, (name, float(pa), float(G["pa"]))
+        assert abs(float(ce) - float(G["ce"])) / abs(float(G["ce"])) < 2e-5, (name, float(ce), float(G["ce"]))
+        (pi * 1.0 + pa * 1.0 + ce * 1.0).backward()
+        assert rel(Sg[0].grad.cpu(), G["d_pi"] + G["d_ce0"]) < 1e-4, name
+        assert rel(Sg[1].grad.cpu(), G["d_ce1"]) < 1e-4, name
+        assert rel(Sg[2].grad.cpu(), G["d_pa"]) < 2e-4, name
+
+
+def test_pixelwise_full_size_properties(ops):
+    """At BASELINE size (8,19,65,129): loss(S,S) == sum of entropies; gradient rows sum to zero; batch linearity."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    S = torch.randn(8, 19, 65, 129, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    T = torch.randn(8, 19, 65, 129, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    l_all = ops.pixelwise_fwd(S, T)
+    l_half = ops.pixelwise_fwd(S[:4].contiguous(memory_format=torch.channels_last), T[:4].contiguous(memory_format=torch.channels_last)) + \
+        ops.pixelwise_fwd(S[4:].contiguous(memory_format=torch.channels_last), T[4:].contiguous(memory_format=torch.channels_last))
+    assert abs(float(l_all) - float(l_half)) / float(l_all) < 1e-6            # batch-summed, not averaged
+    p = torch.softmax(S.double(), 1)
+    ent = -(p * torch.log_softmax(S.double(), 1)).sum() / 65 / 129
+    assert abs(float(ops.pixelwise_fwd(S, S)) - float(ent)) / float(ent) < 1e-5
+    d = ops.pixelwise_bwd(S, T, torch.ones((), device="cuda"))
+    assert float(d.sum(1).abs().max()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- convolutions
+def _conv_ref64(x, w, stride, pad, dil):
+    return F.conv2d(x.double(), w.double(), None, stride, pad, dil)
+
+
+def _tf32_trunc(t):
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+CONV_CASES = [
+    # N, Cin, H, W, Cout, k, stride, pad, dil
+    (1, 32, 8, 16, 32, 1, 1, 0, 1),
+    (2, 64, 9, 13, 64, 3, 1, 1, 1),
+    (1, 128, 17, 19, 256, 3, 1, 2, 2),
+    (1, 256, 12, 9, 512, 3, 1, 4, 4),
+    (2, 64, 33, 31, 128, 3, 2, 1, 1),
+    (2, 128, 33, 31, 256, 1, 2, 0, 1),
+    (1, 512, 9, 9, 19, 1, 1, 0, 1),
+    (1, 100, 10, 11, 72, 3, 1, 1, 1),          # channel counts that are not multiples of 32
+    (2, 1024, 6, 7, 128, 3, 1, 1, 1),          # long K loop (PSP bottleneck shape class)
+    (1, 64, 65, 129, 64, 3, 1, 1, 1),          # the real 1/8-resolution map with its ragged tiles
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_tcgen05(ops, case):
+    N, Cin, H, W, Cout, k, s, p, d = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5
+    ref = _conv_ref64(x, w, s, p, d)
+    xc = ops.to_nhwc(x); wo = ops.weight_ohwi(w)
+    y = ops.conv2d_fwd(xc, wo, s, p, d)
+    yd = ops.conv2d_fwd(xc, wo, s, p, d, force_direct=True)
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    assert rel(yd, ref) < 1e-5, "direct SIMT conv"
+    assert rel(y, ref) < 2e-3, ("tcgen05 TF32 conv", rel(y, ref))          # TF32 operands, fp32 accumulate
+
+
+def test_conv_fwd_epilogue_and_pitch(ops):
+    """folded-BN scale/shift + residual + ReLU, reading a channel slice and writing into a slice of a wider buffer."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    N, Cin, H, W, Cout = 2, 64, 11, 14, 128
+    big = torch.randn(N, H, W, 96, device="cuda", generator=g).permute(0, 3, 1, 2)
+    x = big[:, 32:96]                                                       # pitch 96, offset 32
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / 24
+    sc = torch.rand(Cout, device="cuda", generator=g) + 0.5; sh = torch.randn(Cout, device="cuda", generator=g)
+    res = ops.to_nhwc(torch.randn(N, Cout, H, W, device="cuda", generator=g))
+    obuf = torch.zeros(N, H, W, 160, device="cuda").permute(0, 3, 1, 2)
+    out = obuf[:, 16:16 + Cout]
+    ops.conv2d_fwd(x, ops.weight_ohwi(w), 1, 1, 1, scale=sc, shift=sh, residual=res, act="relu", out=out)
+    ref = torch.relu(_conv_ref64(x, w, 1, 1, 1) * sc.double()[None, :, None, None] + sh.double()[None, :, None, None] + res.double())
+    assert rel(out, ref) < 2e-3
+    assert float(obuf[:, :16].abs().max()) == 0 and float(obuf[:, 16 + Cout:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("case", [(2, 64, 9, 13, 64, 3, 1, 1, 1), (1, 128, 17, 19, 256, 3, 1, 2, 2), (2, 64, 33, 31, 128, 3, 2, 1, 1),
+                                  (2, 128, 33, 31, 256, 1, 2, 0, 1), (1, 256, 12, 9, 512, 3, 1, 4, 4), (1, 512, 9, 9, 128, 1, 1, 0, 1),
+                                  (2, 64, 65, 129, 64, 3, 1, 1, 1)])
+def test_conv_backward(ops, case):
+    N, Cin, H, W, Cout, k, s, p, d = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case) + 1)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).double().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).double().requires_grad_(True)
+    y = F.conv2d(x, w, None, s, p, d)
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(dy.double())
+    xc = ops.to_nhwc(x.detach().float()); dyc = ops.to_nhwc(dy); wo = ops.weight_ohwi(w.detach().float())
+    dw_ref = w.grad.permute(0, 2, 3, 1)
+    assert rel(ops.conv2d_wgrad(xc, dyc, (k, k), s, p, d, force_direct=True), dw_ref) < 1e-4, "direct wgrad"
+    assert rel(ops.conv2d_dgrad(dyc, wo, x.shape, s, p, d, force_direct=True), x.grad) < 1e-5, "direct dgrad"
+    assert rel(ops.conv2d_wgrad(xc, dyc, (k, k), s, p, d), dw_ref) < 2e-3, "tcgen05 wgrad"
+    if s == 1:
+        assert rel(ops.conv2d_dgrad(dyc, wo, x.shape, s, p, d), x.grad) < 2e-3, "tcgen05 dgrad"
+
+
+# ---------------------------------------------------------------------------------------------- pools
+def test_stem_maxpool_and_psp_pyramid(ops):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(2, 16, 22, 30, device="cuda", generator=g).requires_grad_(True)
+    ref = F.max_pool2d(x, 3, 2, 1, ceil_mode=True)
+    y, arg = ops.maxpool_fwd(ops.to_nhwc(x.detach()))
+    assert torch.equal(y, ref)
+    dy = torch.randn(ref.shape, device="cuda", generator=g)
+    ref.backward(dy)
+    assert rel(ops.maxpool_bwd(ops.to_nhwc(dy), arg, x.shape), x.grad) < 1e-6
+    # PSP pyramid pooling + upsampling (networks/pspnet_combine.py:103,110)
+    sizes = [1, 2, 3, 6]
+    f = torch.randn(2, 32, 9, 13, device="cuda", generator=g).requires_grad_(True)
+    pooled = ops.psp_pool_fwd(ops.to_nhwc(f.detach()), sizes)
+    off = 0
+    grads = torch.zeros_like(f)
+    for s in sizes:
+        refp = F.adaptive_avg_pool2d(f, (s, s))
+        mine = pooled[:, off:off + s * s].reshape(2, s, s, 32).permute(0, 3, 1, 2)
+        assert rel(mine, refp) < 1e-6
+        up_ref = F.interpolate(refp, size=(9, 13), mode="bilinear", align_corners=True)
+        buf = torch.zeros(2, 9, 13, 40, device="cuda").permute(0, 3, 1, 2)
+        ops.psp_upsample_fwd(pooled[:, off:off + s * s].contiguous(), s, buf, 8)
+        assert rel(buf[:, 8:40], up_ref) < 1e-5
+        dup = torch.randn(2, 40, 9, 13, device="cuda", generator=g)
+        (gp,) = torch.autograd.grad(up_ref, refp, dup[:, 8:40], retain_graph=True)
+        mine_g = ops.psp_upsample_bwd(ops.to_nhwc(dup), s, 32, 8).reshape(2, s, s, 32).permute(0, 3, 1, 2)
+        assert rel(mine_g, gp) < 1e-5
+        off += s * s
+    dpool = torch.randn(pooled.shape, device="cuda", generator=g)
+    off = 0; tot = 0
+    for s in sizes:
+        refp = F.adaptive_avg_pool2d(f, (s, s))
+        tot = tot + (refp * dpool[:, off:off + s * s].reshape(2, s, s, 32).permute(0, 3, 1, 2)).sum()
+        off += s * s
+    (gf,) = torch.autograd.grad(tot, f)
+    assert rel(ops.psp_pool_bwd(dpool, sizes, f.shape), gf) < 1e-5
+
+
+def test_sgd_step_matches_torch(ops):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    p = torch.randn(10007, device="cuda", generator=g); p0 = p.clone()
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([ref], 0.01, momentum=0.9, weight_decay=5e-4)
+    buf = torch.zeros_like(p); lr = torch.tensor(0.01, device="cuda")
+    for it in range(3):
+        gr = torch.randn(10007, device="cuda", generator=g)
+        ref.grad = gr.clone(); opt.step()
+        ops.sgd_step(p, gr, buf, lr, 0.9, 5e-4, it == 0)
+    assert rel(p, ref.detach()) < 1e-6
