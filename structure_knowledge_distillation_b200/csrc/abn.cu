@@ -144,7 +144,6 @@ nchw_edz_eydz_kernel(const float* __restrict__ z, const float* __restrict__ dz, 
   const int c = blockIdx.x / cl, rank = blockIdx.x % cl;
   const float gamma = weight ? fabsf(weight[c]) + eps : 1.f;
   const float beta = bias ? bias[c] : 0.f;
-  const float rg = 1.f / gamma;
   float s1 = 0.f, s2 = 0.f;
   if (vec) {
     const int S4 = S >> 2;
@@ -155,7 +154,7 @@ nchw_edz_eydz_kernel(const float* __restrict__ z, const float* __restrict__ dz, 
       float4 a = ld_stream(reinterpret_cast<const float4*>(z + off) + s4);
       float4 g = ld_stream(reinterpret_cast<const float4*>(dz + off) + s4);
       s1 += (g.x + g.y) + (g.z + g.w);
-      s2 += ((a.x - beta) * rg * g.x + (a.y - beta) * rg * g.y) + ((a.z - beta) * rg * g.z + (a.w - beta) * rg * g.w);
+      s2 += ((a.x - beta) / gamma * g.x + (a.y - beta) / gamma * g.y) + ((a.z - beta) / gamma * g.z + (a.w - beta) / gamma * g.w);
     }
   } else {
     const long long tot = (long long)N * S;
@@ -163,7 +162,7 @@ nchw_edz_eydz_kernel(const float* __restrict__ z, const float* __restrict__ dz, 
       const int n = (int)(j / S), s = (int)(j - (long long)n * S);
       const size_t off = ((size_t)n * C + c) * S + s;
       const float g = dz[off];
-      s1 += g; s2 += (z[off] - beta) * rg * g;
+      s1 += g; s2 += (z[off] - beta) / gamma * g;
     }
   }
   float2 t = cluster_sum2(s1, s2);
@@ -185,7 +184,7 @@ nchw_backward_kernel(const float* __restrict__ dz, const float* __restrict__ z, 
   if (dx) {
     const float v = var[c];
     const float invstd = (v != 0.f || eps != 0.f) ? 1.f / sqrtf(v + eps) : 0.f;
-    const float mul = gamma * invstd, rg = 1.f / gamma;
+    const float mul = gamma * invstd;
     if (vec) {
       const int S4 = S >> 2;
       const long long tot4 = (long long)N * S4;
@@ -195,8 +194,8 @@ nchw_backward_kernel(const float* __restrict__ dz, const float* __restrict__ z, 
         float4 g = ld_stream(reinterpret_cast<const float4*>(dz + off));
         float4 a = ld_stream(reinterpret_cast<const float4*>(z + off));
         float4 o;
-        o.x = (g.x - e1 - (a.x - beta) * rg * e2) * mul; o.y = (g.y - e1 - (a.y - beta) * rg * e2) * mul;
-        o.z = (g.z - e1 - (a.z - beta) * rg * e2) * mul; o.w = (g.w - e1 - (a.w - beta) * rg * e2) * mul;
+        o.x = (g.x - e1 - (a.x - beta) / gamma * e2) * mul; o.y = (g.y - e1 - (a.y - beta) / gamma * e2) * mul;
+        o.z = (g.z - e1 - (a.z - beta) / gamma * e2) * mul; o.w = (g.w - e1 - (a.w - beta) / gamma * e2) * mul;
         *reinterpret_cast<float4*>(dx + off) = o;
       }
     } else {
@@ -204,7 +203,7 @@ nchw_backward_kernel(const float* __restrict__ dz, const float* __restrict__ z, 
       for (long long j = (long long)blockIdx.y * blockDim.x + threadIdx.x; j < tot; j += (long long)gridDim.y * blockDim.x) {
         const int n = (int)(j / S), s = (int)(j - (long long)n * S);
         const size_t off = ((size_t)n * C + c) * S + s;
-        dx[off] = (dz[off] - e1 - (z[off] - beta) * rg * e2) * mul;
+        dx[off] = (dz[off] - e1 - (z[off] - beta) / gamma * e2) * mul;
       }
     }
   }

@@ -7,7 +7,7 @@
 // Layout: activations NHWC fp32 (row pitch ld*, so channel slices of a concat buffer are addressable in place),
 // weights [Cout][KH][KW][Cin] (K-major), fp32 storage, TF32 tensor-core math with fp32 accumulation in TMEM.
 //
-// One persistent CTA per SM, 6 warps:
+// One persistent CTA per SM, 10 warps:
 //   warp 0   TMA producer  : per (tap, 32-channel chunk) one 4-D box {32ch, BW, BH, 1} of X (the tile is a BH x BW
 //                            rectangle of output pixels; the tap shift / padding / stride live in the box coordinates,
 //                            out-of-bounds = hardware zero fill) + one 3-D box {32ch, 1 tap, BLOCK_N} of W, both
@@ -15,8 +15,10 @@
 //   warp 1   MMA issuer    : 4 x tcgen05.mma.kind::tf32 (M=128, N=BLOCK_N, K=8) per stage, accumulator in TMEM
 //                            (2 accumulator stages x BLOCK_N columns), tcgen05.commit releases smem stages / signals
 //                            the epilogue.
-//   warps 2-5 epilogue     : tcgen05.ld 32x32b -> registers -> fused per-channel scale/shift (folded BN or bias),
-//                            residual add, ReLU / leaky-ReLU, optional RNA rounding to TF32 -> 128-bit global stores.
+//   warps 2-9 epilogue     : two groups of four warps (one per TMEM lane quarter) take alternate 32-column chunks:
+//                            tcgen05.ld 32x32b -> registers -> fused per-channel scale/shift (folded BN or bias, staged
+//                            in smem), residual add, ReLU / leaky-ReLU -> 128B-swizzled smem staging -> TMA store of the
+//                            BH x BW x 32ch box (coalesced, async, hardware-clipped at the ragged edges).
 //                            Overlaps the next tile's MMAs through the second TMEM accumulator stage.
 #include <cuda.h>
 
@@ -31,7 +33,7 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;                 // fp32 elements = 128 B = one swizzle row
 constexpr int kUmmaK = 8;                   // tf32
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kABytes = kBlockM * kBlockK * 4;
 
 struct ConvArgs {
@@ -44,6 +46,7 @@ struct ConvArgs {
   const float* residual; int ldr;
   int act; float slope; int round_out;
   int vec_ok;
+  int tma_store;
 };
 
 template <int BLOCK_N>
@@ -52,29 +55,35 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;       // power of two: 64..512
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kOutStageBytes = kBlockM * 32 * 4;                      // one 128-pixel x 32-channel chunk
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kOutStageBytes + 768 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const ConvArgs a) {
+                      const __grid_constant__ CUtensorMap tmap_y, const ConvArgs a) {
   using C = Cfg<BLOCK_N>;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* out_stage = smem + C::kStages * C::kStageBytes;                   // 2 x 16 KB, 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * C::kOutStageBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [BLOCK_N], 16B aligned
+  float* s_shift = s_scale + BLOCK_N;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_w);
+    if (a.tma_store) ptx::prefetch_tmap(&tmap_y);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_base_slot);
@@ -142,10 +151,15 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9: two groups of four, one warp per TMEM lane quarter) =====================
+    const int ew = warp - 2;
     const int quarter = warp & 3;                              // TMEM lane quarter this warp may access
+    const int group = ew >> 2;                                 // group g takes the 32-column chunks ch = g, g+2, ...
     const int row = quarter * 32 + lane;                       // accumulator row == pixel inside the tile
+    const int etid = ew * 32 + lane;                           // 0..255 over both groups
+    const bool is_store_leader = ((ew & 3) == 0 && lane == 0);
     const int dy = row / a.BW, dx = row - dy * a.BW;
+    uint8_t* stg = out_stage + group * C::kOutStageBytes;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
@@ -155,40 +169,88 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const bool valid = (oy < a.OH) && (ox < a.OW);
       const size_t pix = ((size_t)img * a.OH + oy) * a.OW + ox;
       float* yrow = a.y + pix * a.ldy;
-      const float* rrow = a.residual ? a.residual + pix * a.ldr : nullptr;
+      const float* rrow = (a.residual && valid) ? a.residual + pix * a.ldr : nullptr;
+
+      // per-channel affine of this N tile -> shared memory (ones / zeros when absent, zeros past Cout)
+      ptx::named_bar_sync(3, 256);
+      if (etid < BLOCK_N) {
+        const int c = nt * BLOCK_N + etid;
+        s_scale[etid] = (c < a.Cout) ? (a.scale ? __ldg(a.scale + c) : 1.f) : 0.f;
+        s_shift[etid] = (c < a.Cout && a.shift) ? __ldg(a.shift + c) : 0.f;
+      }
+      ptx::named_bar_sync(3, 256);
 
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      for (int ch = group; ch < BLOCK_N / 32; ch += 2) {
+        const int c0 = nt * BLOCK_N + ch * 32;
+        if (c0 >= a.Cout) break;                                               // CTA-uniform
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + ch * 32, r);
         ptx::tmem_ld_wait();
-        const int c0 = nt * BLOCK_N + ch * 32;
-        if (valid && c0 < a.Cout) {
+        float v[32];
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + ch * 32);
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 sc = sc4[j], sh = sh4[j];
+          v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x);
+          v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+          v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
+          v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+        }
+        if (rrow) {
+          if (a.vec_ok && c0 + 32 <= a.Cout) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(rrow + c0) + j);
+              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (c0 + j < a.Cout) v[j] += __ldg(rrow + c0 + j);
+          }
+        }
+        if (a.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (a.act == ACT_LEAKY) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] < 0.f ? v[j] * a.slope : v[j];
+        } else if (a.act == ACT_ELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] < 0.f ? expm1f(v[j]) : v[j];
+        }
+        if (a.round_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
+        }
+        if (a.tma_store) {
+          // stage the chunk in shared memory (128B-swizzled rows) and let the TMA engine write the BH x BW x 32 box:
+          // fully coalesced, asynchronous, and pixels / channels outside the tensor are clipped by the hardware.
+          if (is_store_leader) ptx::bulk_wait_read<0>();                       // this group's previous store has read the buffer
+          ptx::named_bar_sync(1 + group, 128);
+          uint8_t* srow = stg + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1 + group, 128);
+          if (is_store_leader) {
+            ptx::tma_store_4d(&tmap_y, stg, c0, tx * a.BW, ty * a.BH, img);
+            ptx::bulk_commit();
+          }
+        } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float v[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int c = c0 + j + t;
-              float f = __uint_as_float(r[j + t]);
-              if (c < a.Cout) {
-                if (a.scale) f *= __ldg(a.scale + c);
-                if (a.shift) f += __ldg(a.shift + c);
-                if (rrow) f += __ldg(rrow + c);
-                f = act_fwd(f, a.act, a.slope);
-                if (a.round_out) f = ptx::round_tf32(f);
-              }
-              v[t] = f;
-            }
             const int c = c0 + j;
             if (a.vec_ok && c + 3 < a.Cout) {
-              *reinterpret_cast<float4*>(yrow + c) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(yrow + c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) if (c + t < a.Cout) yrow[c + t] = v[t];
+              for (int t = 0; t < 4; ++t) if (c + t < a.Cout) yrow[c + t] = v[j + t];
             }
           }
         }
@@ -198,6 +260,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (is_store_leader) ptx::bulk_wait<0>();
   }
 
   ptx::tc_fence_before();
@@ -228,10 +291,10 @@ EncodeTiledFn get_encode_tiled() {
 
 
 bool encode(CUtensorMap* m, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-            const cuuint32_t* box, const cuuint32_t* estr, const char* who) {
+            const cuuint32_t* box, const cuuint32_t* estr, const char* who, bool is_output = false) {
   EncodeTiledFn fn = get_encode_tiled();
   if (!fn) { set_error_msg(who, "cuTensorMapEncodeTiled unavailable (no CUDA driver)"); return false; }
-  CUresult r = fn(m, g_tf32_tma_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+  CUresult r = fn(m, (g_tf32_tma_type && !is_output) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                   const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -254,7 +317,7 @@ void pick_rect(int OH, int OW, int stride, int* BH, int* BW) {
 }
 
 template <int BLOCK_N>
-int launch(const CUtensorMap& tx, const CUtensorMap& tw, const ConvArgs& a, cudaStream_t st) {
+int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvArgs& a, cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
   static bool attr = false;
   if (!attr) {
@@ -264,7 +327,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const ConvArgs& a, cuda
   }
   int grid = a.m_tiles * a.n_tiles;
   if (grid > kNumSMs) grid = kNumSMs;
-  conv_fwd_sm100_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, a);
+  conv_fwd_sm100_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, ty, a);
   return finish("skd_conv2d_fwd_sm100");
 }
 
@@ -309,10 +372,19 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
     cuuint32_t estr[3] = {1, 1, 1};
     if (!encode(&tw, 3, w, dims, strides, box, estr, who)) return 0;
   }
+  CUtensorMap ty = tx;
+  a.tma_store = (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15);
+  if (a.tma_store) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)OW * ldy * 4, (cuuint64_t)OH * OW * ldy * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode(&ty, 4, y, dims, strides, box, estr, who, true)) return 0;
+  }
   switch (bn) {
-    case 256: return launch<256>(tx, tw, a, st);
-    case 128: return launch<128>(tx, tw, a, st);
-    case 64: return launch<64>(tx, tw, a, st);
-    default: return launch<32>(tx, tw, a, st);
+    case 256: return launch<256>(tx, tw, ty, a, st);
+    case 128: return launch<128>(tx, tw, ty, a, st);
+    case 64: return launch<64>(tx, tw, ty, a, st);
+    default: return launch<32>(tx, tw, ty, a, st);
   }
 }

@@ -117,9 +117,10 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
           const uint32_t sb = sa + C::kABytes;
 #pragma unroll
           for (int kk = 0; kk < kKPix / 8; ++kk) {
-            // MN-major SW128: LBO = distance between 32-channel chunks, SBO = distance between 8-pixel groups
-            const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 1024, kChunkBytes, 1024);
-            const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 1024, kChunkBytes, 1024);
+            // MN-major tf32 must use the 128B swizzle with 32B atoms (UMMA layout type 1 <-> TMA SWIZZLE_128B_ATOM_32B):
+            // LBO = distance between 32-channel chunks, SBO = distance between 4-pixel groups
+            const uint64_t da = ptx::make_smem_desc(sa + kk * 1024, kChunkBytes, 512, 1);
+            const uint64_t db = ptx::make_smem_desc(sb + kk * 1024, kChunkBytes, 512, 1);
             ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
           }
           ptx::mma_commit(&empty_bar[stage]);
@@ -268,7 +269,7 @@ extern "C" int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, in
     cuuint32_t box[4] = {32, (cuuint32_t)p.BWk, (cuuint32_t)p.BHk, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tdy, dt, 4, const_cast<float*>(dy), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeTiled(dy) failed"); return 0; }
   }
   {
@@ -277,7 +278,7 @@ extern "C" int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, in
     cuuint32_t box[4] = {32, (cuuint32_t)(p.BWk * stride), (cuuint32_t)(p.BHk * stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = enc(&tx, dt, 4, const_cast<float*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeTiled(x) failed"); return 0; }
   }
   WgArgs a;

@@ -1,0 +1,201 @@
+"""`NetModel` -- the reference's training-step entry point (networks/kd_model.py:27-193), B200-native underneath.
+
+Kept surface: NetModel(args), .set_input(data), .forward(), .student_backward(), .discriminator_backward(),
+.optimize_parameters(), .adjust_learning_rate(base_lr, optimizer, i_iter), .lr_poly, .print_info, .save_ckpt,
+.evalute_model; attributes .student .teacher .G_solver .D_solver .preds_S .preds_T .G_loss .mc_G_loss .pi_G_loss
+.pa_G_loss .D_loss (train_and_eval.py:19-30 reads them).
+
+What changed underneath:
+  * single-process nn.DataParallel replicas + per-step parameter broadcast (utils/parallel.py) -> one process per GPU,
+    persistent replicas, ONE NCCL all-reduce (mean) of the flat student-gradient buffer per step (+ one for D when Ho);
+    per-rank loss on the local shard and averaged gradients == the reference's mean-over-GPUs semantics
+    (utils/parallel.py:155);
+  * scalar logging is lazy: the five `.item()` host syncs per step (kd_model.py:130-164) become device scalars that are
+    only read when print_info()/the attribute is used;
+  * the discarded teacher cross-entropy (kd_model.py:129) is not computed.
+"""
+import logging
+import os
+import os.path as osp
+
+import torch
+import torch.distributed as dist
+
+from ..optim import FlatSGD
+from ..utils.criterion import (CriterionAdditionalGP, CriterionAdv, CriterionAdvForG, CriterionDSN,
+                               CriterionPairWiseforWholeFeatAfterPool, CriterionPixelWise)
+from .pspnet_combine import BasicBlock, Bottleneck, Res_pspnet
+from .sagan_models import Discriminator
+
+
+class _LazyScalar:
+    """Device scalar that turns into a Python float only when somebody looks at it."""
+
+    def __init__(self, t):
+        self.t = t.detach()
+
+    def __float__(self):
+        return float(self.t)
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def __repr__(self):
+        return repr(float(self))
+
+    def item(self):
+        return float(self)
+
+
+def _arg(args, name, default):
+    return getattr(args, name, default)
+
+
+class NetModel():
+    def name(self):
+        return 'kd_seg'
+
+    def __init__(self, args):
+        self.args = args
+        device = torch.device(_arg(args, "device", "cuda"))
+        if device.type != "cuda":
+            raise RuntimeError("NetModel runs on CUDA (sm_100a) only; there is no CPU path")
+        self.device = device
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+        student = Res_pspnet(BasicBlock, [2, 2, 2, 2], num_classes=args.classes_num)
+        self._load(student, _arg(args, "S_ckpt_path", None), _arg(args, "student_pretrain_model_imgnet", None))
+        self.student = student.float().to(device).train()
+        self.parallel_student = self.student
+
+        teacher = Res_pspnet(Bottleneck, [3, 4, 23, 3], num_classes=args.classes_num)
+        self._load_teacher(teacher, _arg(args, "T_ckpt_path", None))
+        self.teacher = teacher.float().to(device).eval()
+        for p in self.teacher.parameters():
+            p.requires_grad_(False)
+        self.parallel_teacher = self.teacher
+
+        D_model = Discriminator(args.preprocess_GAN_mode, args.classes_num, args.batch_size, args.imsize_for_adv, args.adv_conv_dim)
+        self.D_model = D_model.float().to(device).train()
+        self.parallel_D = self.D_model
+
+        self.G_solver = FlatSGD([p for p in self.student.parameters() if p.requires_grad], args.lr_g, momentum=args.momentum,
+                                weight_decay=args.weight_decay)
+        self.D_solver = FlatSGD([p for p in self.D_model.parameters() if p.requires_grad], args.lr_d, momentum=args.momentum,
+                                weight_decay=args.weight_decay)
+        self.best_mean_IU = _arg(args, "best_mean_IU", 0.0)
+
+        self.criterion = CriterionDSN()
+        self.criterion_pixel_wise = CriterionPixelWise()
+        self.criterion_pair_wise_for_interfeat = CriterionPairWiseforWholeFeatAfterPool(scale=args.pool_scale, feat_ind=-5)
+        self.criterion_adv = CriterionAdv(args.adv_loss_type)
+        if args.adv_loss_type == 'wgan-gp':
+            self.criterion_AdditionalGP = CriterionAdditionalGP(self.parallel_D, args.lambda_gp)
+        self.criterion_adv_for_G = CriterionAdvForG(args.adv_loss_type)
+
+        self.mc_G_loss = 0.0
+        self.pi_G_loss = 0.0
+        self.pa_G_loss = 0.0
+        self.D_loss = 0.0
+        self.G_loss = 0.0
+        snap = _arg(args, "snapshot_dir", None)
+        if snap and not os.path.exists(snap):
+            os.makedirs(snap, exist_ok=True)
+
+    # ---- checkpoint helpers (utils/utils.py:73-127 semantics: key remap for the teacher, key intersection for ImageNet)
+    @staticmethod
+    def _load_teacher(model, path):
+        if not path or not os.path.exists(path):
+            logging.info("=> no teacher ckpt find")
+            return
+        saved = torch.load(path, map_location="cpu")
+        new = model.state_dict()
+        for k, v in saved.items():
+            if k.startswith('fc.'):
+                continue
+            if k.startswith('head.0.'):
+                new['pspmodule.' + k[7:]] = v
+            elif k.startswith('head.1.'):
+                new['head.' + k[7:]] = v
+            else:
+                new[k] = v
+        model.load_state_dict(new)
+
+    @staticmethod
+    def _load(model, ckpt_dir, imagenet):
+        if imagenet and os.path.isfile(str(imagenet)):
+            saved = torch.load(imagenet, map_location="cpu")
+            cur = model.state_dict()
+            cur.update({k: v for k, v in saved.items() if k in cur})
+            model.load_state_dict(cur)
+
+    # ---- the reference's step API ------------------------------------------------------------------------
+    def set_input(self, data):
+        images, labels = data[0], data[1]
+        self.images = images.to(self.device, non_blocking=True)
+        self.labels = labels.long().to(self.device, non_blocking=True)
+
+    def lr_poly(self, base_lr, iter, max_iter, power):
+        return base_lr * ((1 - float(iter) / max_iter) ** (power))
+
+    def adjust_learning_rate(self, base_lr, optimizer, i_iter):
+        lr = self.lr_poly(base_lr, i_iter, self.args.num_steps, self.args.power)
+        optimizer.param_groups[0]['lr'] = lr
+        return lr
+
+    def forward(self):
+        with torch.no_grad():
+            self.preds_T = self.parallel_teacher.eval()(self.images)
+        self.preds_S = self.parallel_student.train()(self.images)
+
+    def student_backward(self):
+        args = self.args
+        temp = self.criterion(self.preds_S, self.labels)
+        self.mc_G_loss = _LazyScalar(temp)
+        G_loss = temp
+        if args.pi == True:
+            temp = args.lambda_pi * self.criterion_pixel_wise(self.preds_S, self.preds_T)
+            self.pi_G_loss = _LazyScalar(temp)
+            G_loss = G_loss + temp
+        if args.pa == True:
+            temp1 = self.criterion_pair_wise_for_interfeat(self.preds_S, self.preds_T)
+            self.pa_G_loss = _LazyScalar(temp1)
+            G_loss = G_loss + args.lambda_pa * temp1
+        if args.ho == True:
+            d_out_S = self.parallel_D(self.preds_S[0])
+            G_loss = G_loss + args.lambda_d * self.criterion_adv_for_G(d_out_S, d_out_S)
+        G_loss.backward()
+        self.G_loss = _LazyScalar(G_loss)
+
+    def discriminator_backward(self):
+        self.D_solver.zero_grad()
+        args = self.args
+        d_out_T = self.parallel_D(self.preds_T[0].detach())
+        d_out_S = self.parallel_D(self.preds_S[0].detach())
+        d_loss = args.lambda_d * self.criterion_adv(d_out_S, d_out_T)
+        if args.adv_loss_type == 'wgan-gp':
+            d_loss = d_loss + args.lambda_d * self.criterion_AdditionalGP(self.preds_S, self.preds_T)
+        d_loss.backward()
+        self.D_loss = _LazyScalar(d_loss)
+        self.D_solver.all_reduce_grads(self.world)
+        self.D_solver.step()
+
+    def optimize_parameters(self):
+        self.forward()
+        self.G_solver.zero_grad()
+        self.student_backward()
+        self.G_solver.all_reduce_grads(self.world)       # the one collective of the path (teacher is frozen)
+        self.G_solver.step()
+        if self.args.ho == True:
+            self.discriminator_backward()
+
+    def evalute_model(self, model, loader, gpu_id, input_size, num_classes, whole):
+        raise NotImplementedError("evaluation (networks/evaluate.py) is outside the distillation hot path; see DESIGN.md")
+
+    def print_info(self, epoch, step):
+        logging.info('step:{:5d} G_lr:{:.6f} G_loss:{:.5f}(mc:{:.5f} pixelwise:{:.5f} pairwise:{:.5f}) D_lr:{:.6f} D_loss:{:.5f}'.format(
+            step, self.G_solver.param_groups[-1]['lr'], float(self.G_loss), float(self.mc_G_loss), float(self.pi_G_loss),
+            float(self.pa_G_loss), self.D_solver.param_groups[-1]['lr'], float(self.D_loss)))
+
+    def save_ckpt(self, epoch, step, mean_IU, IU_array):
+        torch.save(self.student.state_dict(), osp.join(self.args.snapshot_dir, 'CS_scenes_' + str(step) + '_' + str(mean_IU) + '.pth'))

@@ -1,0 +1,81 @@
+"""Momentum-SGD over ONE flat parameter / gradient / momentum buffer (the reference's optim.SGD of
+networks/kd_model.py:74-75: momentum 0.9, weight decay on every parameter, lr written to param_groups[0]['lr']).
+
+Parameters and their .grad become views into the flat buffers (layouts preserved), so
+  * G_solver.step() is one fused kernel (csrc/pool.cu: sgd_kernel) instead of a per-tensor foreach,
+  * zero_grad() is one memset,
+  * the data-parallel exchange is ONE NCCL all-reduce of the flat gradient buffer; the 1/world averaging is folded into
+    the update kernel (grad_scale).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def _dense(t):
+    """non-overlapping and dense: some permutation of the dims is contiguous"""
+    dims = sorted([(st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1], reverse=True)
+    expect = 1
+    for st, sz in reversed(dims):
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+class FlatSGD:
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("optimizer got an empty parameter list")
+        dev = self.params[0].device
+        self.param_groups = [dict(params=self.params, lr=lr, initial_lr=lr, momentum=momentum, weight_decay=weight_decay)]
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4                       # keep every tensor 16-byte aligned
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self._views = []
+        for p, off in zip(self.params, offs):
+            src = p.data
+            if src.dtype != torch.float32 or not _dense(src):
+                raise ValueError("FlatSGD needs dense fp32 parameters")
+            dst = torch.as_strided(self.flat_p, src.shape, src.stride(), off)
+            dst.copy_(src)
+            p.data = dst
+            g = torch.as_strided(self.flat_g, src.shape, src.stride(), off)
+            p.grad = g
+            self._views.append(g)
+        self.lr_dev = torch.tensor(float(lr), device=dev, dtype=torch.float32)
+        self.steps = 0
+        self.grad_scale = 1.0
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_g.zero_()
+        for p, g in zip(self.params, self._views):
+            if p.grad is not g:                                      # somebody detached it: re-attach the flat view
+                p.grad = g
+
+    def all_reduce_grads(self, world):
+        """utils/parallel.py:54-63,155 semantics: mean over ranks of per-rank gradients."""
+        if world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+            self.grad_scale = 1.0 / world
+        else:
+            self.grad_scale = 1.0
+
+    def step(self):
+        g = self.param_groups[0]
+        self.lr_dev.fill_(float(g['lr']))
+        ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.lr_dev, g['momentum'], g['weight_decay'], self.steps == 0,
+                     self.grad_scale)
+        self.steps += 1
+
+    def state_dict(self):
+        return dict(momentum=self.flat_m.clone(), steps=self.steps, lr=self.param_groups[0]['lr'])
+
+    def load_state_dict(self, sd):
+        self.flat_m.copy_(sd['momentum']); self.steps = sd['steps']; self.param_groups[0]['lr'] = sd['lr']
