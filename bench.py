@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- distillation-step images/sec at 512x1024 (Pi+Pa+Ho), BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (one process per GPU; under torchrun for N > 1)
+  python bench.py --impl reference ...                      the reference's own algorithm on the box's host cores
+
+One "step" = NetModel.optimize_parameters(): frozen PSPNet-101 teacher forward, ResNet18-PSP student forward, CE+Pi+Pa+Ho
+losses, student backward, SGD step, discriminator step (WGAN-GP) -- nothing skipped.  Workload = BASELINE.json
+configs[2]: batch 8 per GPU at 512x1024, synthetic tensors, random-init weights (no dataset / checkpoints offline).
+
+Printed JSON (rank 0, one line):
+  value  images/s with the batch already resident in HBM (CUDA events, max over ranks);
+  e2e    same step through the public API from pinned HOST buffers: per step an H2D copy of images+labels and a D2H read
+         of the loss inside the timed region;
+  roofline  the dominant kernel (tcgen05 implicit-GEMM conv, fwd+dgrad launches): algorithmic FLOP / CUDA-event time of
+            every launch of it inside the timed region, against the measured tensor peak;
+  cpu_baseline  oracle/port.py (CPU restatement pinned to the reference) on a bounded sample, N=1 rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, BATCH_PER_GPU = 512, 1024, 8
+METRIC = "distillation-step images/sec at 512x1024 (Pi+Pa+Ho)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def synthetic(batch, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(batch, 3, H, W, generator=g)
+    labels = torch.randint(0, 19, (batch, H, W), generator=g)
+    labels[torch.rand(batch, H, W, generator=g) < 0.05] = 255
+    return images, labels
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own algorithm (oracle/port.py: CPU restatement pinned against /root/reference by golden fixtures;
+    /root/reference itself does not exist on the GPU box) on all host threads.  Bounded sample: batch 1 per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import cases, port
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = port.StepConfig(pi=True, pa=True, ho=True, adv_type="wgan-gp")
+    teacher, student, D = cases.build_models(seed=0, with_D=True)
+    g_opt, d_opt = port.make_optimizers(student, D, cfg)
+    images, labels = synthetic(1, 0)
+    alpha = torch.rand(1, 1, 1, 1)
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        port.distill_step(teacher, student, D, images, labels, cfg, g_opt, d_opt, gp_alpha=alpha)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        port.distill_step(teacher, student, D, images, labels, cfg, g_opt, d_opt, gp_alpha=alpha)
+    dt = (time.perf_counter() - t0) / steps
+    v = 1.0 / dt
+    sample = "batch 1 of the same 512x1024 Pi+Pa+Ho(wgan-gp) step, %d timed steps after %d warm-up, fp32 torch CPU, %d threads" % (steps, warm, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[2]: ResNet18 student + PSPNet-101 teacher, Pi+Pa+Ho, 512x1024 (bounded sample: batch 1)"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline_leg():
+    import torch
+    from oracle import cases, port
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = port.StepConfig(pi=True, pa=True, ho=True, adv_type="wgan-gp")
+    teacher, student, D = cases.build_models(seed=0, with_D=True)
+    g_opt, d_opt = port.make_optimizers(student, D, cfg)
+    images, labels = synthetic(1, 0)
+    alpha = torch.rand(1, 1, 1, 1)
+    port.distill_step(teacher, student, D, images, labels, cfg, g_opt, d_opt, gp_alpha=alpha)
+    t0 = time.perf_counter()
+    port.distill_step(teacher, student, D, images, labels, cfg, g_opt, d_opt, gp_alpha=alpha)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "oracle/port.py (CPU restatement of the reference step), batch 1 @512x1024 Pi+Pa+Ho, 1 timed step after 1 warm-up, %d threads" % cores}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from structure_knowledge_distillation_b200 import ops
+    from structure_knowledge_distillation_b200._cabi import lib
+    from structure_knowledge_distillation_b200.networks.kd_model import NetModel
+    from structure_knowledge_distillation_b200.utils.train_options import make_args
+
+    torch.manual_seed(0)                                          # identical replicas on every rank
+    margs = make_args(batch_size=BATCH_PER_GPU, pi=True, pa=True, ho=True, adv_loss_type="wgan-gp", gpu_num=world)
+    model = NetModel(margs)
+    # eval-mode BN of the frozen teacher must not be the identity
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for m in model.teacher.modules():
+        if hasattr(m, "running_var"):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, device="cuda", generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, device="cuda", generator=g) + 0.5)
+    images, labels = synthetic(BATCH_PER_GPU, 100 + rank)
+    pin_i, pin_l = images.pin_memory(), labels.pin_memory()
+    dev_i, dev_l = images.cuda(), labels.cuda()
+    L = lib()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, body):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(k):
+            body(i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def step_resident(i):
+        model.adjust_learning_rate(margs.lr_g, model.G_solver, i)
+        model.adjust_learning_rate(margs.lr_d, model.D_solver, i)
+        model.images, model.labels = dev_i, dev_l
+        model.optimize_parameters()
+
+    sink = []
+
+    def step_e2e(i):
+        model.adjust_learning_rate(margs.lr_g, model.G_solver, i)
+        model.adjust_learning_rate(margs.lr_d, model.D_solver, i)
+        model.set_input((pin_i, pin_l, None, None))               # H2D from pinned host memory, every step
+        model.optimize_parameters()
+        sink.append(float(model.G_loss))                          # D2H read of the step's loss
+
+    for i in range(args.warmup):
+        step_resident(i)
+
+    clocks = ClockSampler(local_rank)
+    conv_log = []
+    ops.CONV_EVENT_LOG = conv_log                                  # ops.conv2d_fwd records (start, end, flops) per tcgen05 launch
+    launches0 = L.skd_kernel_launches()
+    if rank == 0:
+        clocks.start()
+    ms = timed(args.steps, step_resident)
+    launches = L.skd_kernel_launches() - launches0
+    ops.CONV_EVENT_LOG = None
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e = timed(args.steps, step_e2e)
+
+    total_images = BATCH_PER_GPU * world * args.steps
+    value = total_images / (ms / 1e3)
+    e2e = total_images / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    tf32_peak = peaks["bf16_sus"] / 2.0                            # kind::tf32 issues at half the bf16 rate
+    conv_ms = sum(s.elapsed_time(e) for s, e, _ in conv_log)
+    conv_flop = sum(f for _, _, f in conv_log)
+    achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "conv_fwd_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    out = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[2]: ResNet18-PSP student + PSPNet-101 teacher, Pi+Pa+Ho (wgan-gp), batch 8/GPU at 512x1024, pool_scale 0.5",
+                   "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d" % world,
+                   "l2": "per-step working set (activations ~10 GB) is far larger than the 126 MB L2: no flush needed"},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": pin_i.numel() * 4 + pin_l.numel() * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "conv_fwd_sm100_kernel (tcgen05 implicit GEMM: teacher fwd, student fwd, student dgrad)",
+                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak if tf32_peak else None,
+                     "peak_source": "%s bf16 sustained cuBLAS peak / 2 (TF32 operands)" % peaks["src"], "traffic": traffic,
+                     "launches_timed": len(conv_log), "share_of_step": conv_ms / ms if ms else None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_leg()
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@ extern "C" {
 
 const char* skd_last_error(void);
 int skd_version(void);
+long long skd_kernel_launches(void);   /* number of kernels this library has launched in this process */
 
 /* ---- A. InPlace-ABN native ABI: one-for-one replacements of libs/src/bn.h:7-19 ((N, C, S) NCHW views) ---- */
 /* replaces _bn_mean_var_cuda  (bn.h:7,  bn.cu:125-138,237-250): per-channel mean and BIASED variance */

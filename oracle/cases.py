@@ -58,6 +58,12 @@ STEP_CASES = {
     "pi_pa_ho_wgangp_512": dict(batch=1, h=512, w=512, cfg=dict(pi=True, pa=True, ho=True, adv_type="wgan-gp")),
 }
 
+# BASELINE.json configs[2] at full size (batch 8 @ 512x1024, Pi+Pa+Ho, wgan-gp): generated once by
+# `python -m oracle.make_golden --full` (several minutes of CPU), checked on the B200 by tests/test_step_gpu.py.
+FULL_CASES = {
+    "baseline_cfg3_b8_512x1024": dict(batch=8, h=512, w=1024, cfg=dict(pi=True, pa=True, ho=True, adv_type="wgan-gp")),
+}
+
 
 def grad_digest(named_params, k=16):
     """Small fingerprint of each gradient: l2 norm, sum, and k strided samples."""

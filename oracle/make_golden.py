@@ -145,9 +145,9 @@ def _ref_step(ref, teacher, student, D, images, labels, cfg, alpha):
     return out
 
 
-def step_goldens(ref):
+def step_goldens(ref, table=None, check_port=True):
     res = {}
-    for name, spec in cases.STEP_CASES.items():
+    for name, spec in (table or cases.STEP_CASES).items():
         t0 = time.time()
         cfg = port.StepConfig(**spec["cfg"])
         teacher, student, D = cases.build_models(seed=0, with_D=cfg.ho)
@@ -171,6 +171,10 @@ def step_goldens(ref):
             cd = port.ChannelDropout(0.1); cd.injected = m
             holder[idx] = cd
         gold = _ref_step(ref, r_teacher, r_student, r_D, images, labels, cfg, alpha)
+        if not check_port:
+            print("step", name, {k: round(v, 6) for k, v in gold.items() if isinstance(v, float)}, "%.1fs" % (time.time() - t0))
+            res[name] = gold
+            continue
         mine = port.distill_step(teacher, student, D, images, labels, cfg, gp_alpha=alpha)
         for k in ("ce", "pi", "pa", "adv_g", "G", "D"):
             if k in gold:
@@ -188,6 +192,9 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref = refshim.load_reference()
     torch.set_num_threads(os.cpu_count())
+    if "--full" in sys.argv:
+        torch.save(step_goldens(ref, cases.FULL_CASES, check_port=False), os.path.join(GOLDEN_DIR, "steps_full.pt"))
+        return
     torch.save(dict(criterion=criterion_goldens(ref), adv=adv_goldens(ref)), os.path.join(GOLDEN_DIR, "criteria.pt"))
     torch.save(discriminator_golden(ref), os.path.join(GOLDEN_DIR, "discriminator.pt"))
     torch.save(step_goldens(ref), os.path.join(GOLDEN_DIR, "steps.pt"))

@@ -586,7 +586,7 @@ extern "C" int skd_abn_stats_nhwc(long long P, int C, const float* x, const floa
   nhwc_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(x, reinterpret_cast<const float2*>(workspace), splits, C,
                                                              (float)P, weight, bias, eps, momentum, running_mean,
                                                              running_var, mean, var, scale, shift);
-  return finish("skd_abn_stats_nhwc");
+  return finish("skd_abn_stats_nhwc", 2);
 }
 
 extern "C" int skd_abn_fold(int C, const float* mean, const float* var, const float* weight, const float* bias, float eps,
@@ -618,7 +618,7 @@ extern "C" int skd_abn_bwd_reduce_nhwc(long long P, int C, int S, const float* x
                                                                mean, var, eps, act, slope, chan_mul);
   nhwc_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float2*>(workspace), splits, C, (float)P,
                                                            weight, edz, eydz, dweight, dbias);
-  return finish("skd_abn_bwd_reduce_nhwc");
+  return finish("skd_abn_bwd_reduce_nhwc", 2);
 }
 
 extern "C" int skd_abn_bwd_dx_nhwc(long long P, int C, int S, const float* x, const float* out, const float* dout,

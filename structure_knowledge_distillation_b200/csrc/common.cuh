@@ -15,9 +15,11 @@ void set_error_msg(const char* where, const char* msg);
 extern int g_tf32_tma_type;
 
 // Reference convention (libs/src/bn.cu:244-249): every launcher returns 1 on success, 0 on a CUDA error.
-inline int finish(const char* where) {
+extern unsigned long long g_kernel_launches;     // kernels this library launched (skd_kernel_launches())
+inline int finish(const char* where, int kernels = 1) {
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error(where, err); return 0; }
+  g_kernel_launches += (unsigned long long)kernels;
   return 1;
 }
 

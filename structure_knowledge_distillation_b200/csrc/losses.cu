@@ -424,7 +424,7 @@ extern "C" int skd_pixelwise_fwd(int N, int C, int HW, const float* S, long long
   const int blocks = red_blocks((long long)N * HW);
   pixelwise_fwd_kernel<<<blocks, 256, 0, st>>>(S, T, N, C, HW, Strides{s_sn, s_sc, s_sp}, Strides{t_sn, t_sc, t_sp}, workspace);
   finalize_sum_kernel<<<1, 256, 0, st>>>(workspace, blocks, (double)inv_hw, loss, nullptr, 0, nullptr);
-  return finish("skd_pixelwise_fwd");
+  return finish("skd_pixelwise_fwd", 2);
 }
 
 extern "C" int skd_pixelwise_bwd(int N, int C, int HW, const float* S, long long s_sn, long long s_sc, long long s_sp,
@@ -447,7 +447,7 @@ extern "C" int skd_dsn_ce_fwd(int N, int C, int h, int w, int H, int W, const fl
   dsn_ce_fwd_kernel<<<blocks, 256, 0, st>>>(L0, L1, Strides{a_sn, a_sc, a_sp}, Strides{b_sn, b_sc, b_sp}, labels, N, C, h, w,
                                            H, W, ignore_index, w0, w1, workspace, workspace + blocks);
   finalize_sum_kernel<<<1, 256, 0, st>>>(workspace, blocks, 1.0, loss, workspace + blocks, 1, count);
-  return finish("skd_dsn_ce_fwd");
+  return finish("skd_dsn_ce_fwd", 2);
 }
 
 extern "C" long long skd_dsn_ce_bwd_workspace_floats(int N, int C, int w, int H, int heads) {
@@ -473,7 +473,7 @@ extern "C" int skd_dsn_ce_bwd(int N, int C, int h, int w, int H, int W, const fl
   const long long tot = (long long)heads * N * h * C * w;
   dsn_ce_bwd_cols_kernel<<<red_blocks(tot), 256, 0, st>>>(workspace, d0, L1 ? d1 : nullptr, Strides{a_sn, a_sc, a_sp},
                                                          Strides{b_sn, b_sc, b_sp}, N, C, h, w, H, grad_out, count, w0, w1);
-  return finish("skd_dsn_ce_bwd");
+  return finish("skd_dsn_ce_bwd", 2);
 }
 
 extern "C" int skd_pairwise_pool(int N, int C, int H, int W, const float* F, long long sn, long long sc, long long sp,
@@ -482,7 +482,7 @@ extern "C" int skd_pairwise_pool(int N, int C, int H, int W, const float* F, lon
   const int nh = (H + ph - 1) / ph, nw = (W + pw - 1) / pw;
   pa_pool_kernel<<<dim3(nh * nw, N, (C + 63) / 64), 256, 0, st>>>(F, Strides{sn, sc, sp}, C, H, W, ph, pw, nh, nw, pooled, argmax);
   pa_rnorm_kernel<<<N * nh * nw, 32, 0, st>>>(pooled, C, rnorm);
-  return finish("skd_pairwise_pool");
+  return finish("skd_pairwise_pool", 2);
 }
 
 extern "C" long long skd_pairwise_gram_partials(int N, int nodes) {
@@ -497,7 +497,7 @@ extern "C" int skd_pairwise_gram(int N, int nodes, int CS, int CT, const float* 
   pa_gram_kernel<<<dim3(t, t, N), 256, 0, st>>>(pooled_S, pooled_T, rnorm_S, rnorm_T, CS, CT, nodes, E, workspace);
   const double scale = 1.0 / ((double)nodes * (double)nodes) / (double)N;          // utils.py:181
   finalize_sum_kernel<<<1, 256, 0, st>>>(workspace, N * t * t, scale, loss, nullptr, 0, nullptr);
-  return finish("skd_pairwise_gram");
+  return finish("skd_pairwise_gram", 2);
 }
 
 extern "C" int skd_pairwise_bwd(int N, int nodes, int CS, const float* E, const float* pooled_S, const float* rnorm_S,
@@ -506,5 +506,5 @@ extern "C" int skd_pairwise_bwd(int N, int nodes, int CS, const float* E, const 
   const int t = (nodes + kPT - 1) / kPT;
   pa_bwd_kernel<<<dim3((CS + kPT - 1) / kPT, t, N), 256, 0, st>>>(E, pooled_S, rnorm_S, CS, nodes, N, grad_out, dpooled);
   pa_scatter_kernel<<<red_blocks((long long)N * nodes * CS), 256, 0, st>>>(dpooled, argmax, CS, nodes, N, dF, Strides{sn, sc, sp});
-  return finish("skd_pairwise_bwd");
+  return finish("skd_pairwise_bwd", 2);
 }

@@ -8,6 +8,7 @@
 namespace skd {
 static thread_local char g_err[256] = "";
 int g_tf32_tma_type = 1;
+unsigned long long g_kernel_launches = 0;
 void set_error(const char* where, cudaError_t err) { snprintf(g_err, sizeof g_err, "%s: %s", where, cudaGetErrorString(err)); }
 void set_error_msg(const char* where, const char* msg) { snprintf(g_err, sizeof g_err, "%s: %s", where, msg); }
 }  // namespace skd
@@ -35,6 +36,7 @@ int blocks_for(long long n) { long long b = (n + 255) / 256; if (b > kNumSMs * 1
 
 extern "C" const char* skd_last_error(void) { return skd::g_err; }
 extern "C" int skd_version(void) { return 100; }
+extern "C" long long skd_kernel_launches(void) { return (long long)skd::g_kernel_launches; }
 extern "C" void skd_set_tf32_tma_type(int use_tfloat32_type) { skd::g_tf32_tma_type = use_tfloat32_type ? 1 : 0; }
 
 extern "C" int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w, float* wt, int round_tf32, cudaStream_t st) {

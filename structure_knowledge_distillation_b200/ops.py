@@ -9,6 +9,9 @@ from ._cabi import lib
 
 ACT = {"none": 0, "leaky_relu": 1, "elu": 2, "relu": 3}
 
+# bench.py sets this to a list to time every tcgen05 conv launch with CUDA events: (start, end, algorithmic FLOP)
+CONV_EVENT_LOG = None
+
 
 def _p(t):
     return None if t is None else t.data_ptr()
@@ -162,8 +165,15 @@ def conv2d_fwd(x, w_ohwi, stride, pad, dil, scale=None, shift=None, residual=Non
                                 _p(shift), ACT[act], slope, _st())
         return out
     ldr = nhwc_meta(residual)[4] if residual is not None else 0
+    log = CONV_EVENT_LOG
+    if log is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     L.skd_conv2d_fwd_sm100(n, h, w, cin, cout, kh, kw, stride, pad, dil, _p(x), ldx, _p(w_ohwi), _p(out), ldy, _p(scale),
                            _p(shift), _p(residual), ldr, ACT[act], slope, int(round_tf32), _st())
+    if log is not None:
+        ev1.record()
+        log.append((ev0, ev1, 2.0 * n * oh * ow * cout * cin * kh * kw))
     return out
 
 
@@ -177,8 +187,15 @@ def conv2d_dgrad(dy, w_ohwi, x_shape, stride, pad, dil, round_tf32=False, force_
     if stride == 1 and not force_direct and cout % 4 == 0 and ldy % 4 == 0:
         wt = torch.empty((cin, kh, kw, cout), device=dy.device, dtype=torch.float32)
         L.skd_weight_flip_transpose(cout, cin, kh, kw, _p(w_ohwi), _p(wt), 0, _st())
+        log = CONV_EVENT_LOG
+        if log is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         L.skd_conv2d_fwd_sm100(n, doh, dow, cout, cin, kh, kw, 1, dil * (kh - 1) - pad, dil, _p(dy), ldy, _p(wt), _p(dx), cin,
                                None, None, None, 0, 0, 0.0, int(round_tf32), _st())
+        if log is not None:
+            ev1.record()
+            log.append((ev0, ev1, 2.0 * n * h * w * cin * cout * kh * kw))
     else:
         L.skd_conv2d_dgrad_direct(n, h, w, cin, cout, kh, kw, stride, pad, dil, _p(dy), ldy, _p(w_ohwi), _p(dx), cin, _st())
     return dx

@@ -15,7 +15,7 @@ def _build(name):
     from oracle import cases, port
     from structure_knowledge_distillation_b200.networks.kd_model import NetModel
     from structure_knowledge_distillation_b200.utils.train_options import make_args
-    spec = cases.STEP_CASES[name]
+    spec = cases.STEP_CASES.get(name) or cases.FULL_CASES[name]
     cfg = port.StepConfig(**spec["cfg"])
     teacher, student, D = cases.build_models(seed=0, with_D=True)
     if not cfg.ho:
@@ -44,9 +44,11 @@ def _relerr(a, b):
     return abs(float(a) - float(b)) / max(abs(float(b)), 1e-12)
 
 
-@pytest.mark.parametrize("name", ["cfg1_pi_64", "pi_pa_96x128", "pi_pa_ho_hinge_512", "pi_pa_ho_wgangp_512"])
+@pytest.mark.parametrize("name", ["cfg1_pi_64", "pi_pa_96x128", "pi_pa_ho_hinge_512", "pi_pa_ho_wgangp_512",
+                                  "baseline_cfg3_b8_512x1024"])
 def test_distillation_step_matches_reference_golden(name):
-    gold = torch.load(os.path.join(ROOT, "tests", "golden", "steps.pt"), weights_only=False)[name]
+    fname = "steps_full.pt" if name.startswith("baseline") else "steps.pt"
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", fname), weights_only=False)[name]
     m, cfg = _build(name)
     m.forward()
     m.G_solver.zero_grad()
