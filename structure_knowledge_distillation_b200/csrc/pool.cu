@@ -96,24 +96,34 @@ __device__ __forceinline__ void bin_of(const Pyramid& p, int bin, int& lvl, int&
 __device__ __forceinline__ int bin_lo(int i, int in, int s) { return (i * in) / s; }                  // floor
 __device__ __forceinline__ int bin_hi(int i, int in, int s) { return ((i + 1) * in + s - 1) / s; }    // ceil
 
-// pooled[n][bin][c]; block = 64 channel lanes (x4 channels each... scalar here) x 4 pixel lanes
-__global__ void __launch_bounds__(256)
+// pooled[n][bin][c]; block = 64 channel lanes x 16 pixel lanes (4 independent loads in flight per thread)
+constexpr int kPoolLanes = 16;
+__global__ void __launch_bounds__(64 * kPoolLanes)
 psp_pool_fwd_kernel(const float* __restrict__ x, int pitch, int C, int H, int W, Pyramid p, float* __restrict__ pooled) {
-  __shared__ float sv[256];
+  __shared__ float sv[64 * kPoolLanes];
   const int bin = blockIdx.x, n = blockIdx.y, cx = threadIdx.x & 63, lane = threadIdx.x >> 6, c = blockIdx.z * 64 + cx;
   int lvl, by, bx; bin_of(p, bin, lvl, by, bx);
   const int s = p.size[lvl];
   const int y0 = bin_lo(by, H, s), y1 = bin_hi(by, H, s), x0 = bin_lo(bx, W, s), x1 = bin_hi(bx, W, s);
   const int ww = x1 - x0, cnt = (y1 - y0) * ww;
-  float a = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (c < C) {
     const float* base = x + (size_t)n * H * W * pitch + c;
-    for (int k = lane; k < cnt; k += 4) a += __ldg(base + ((size_t)(y0 + k / ww) * W + x0 + k % ww) * pitch);
+    int k = lane;
+    for (; k + 3 * kPoolLanes < cnt; k += 4 * kPoolLanes) {
+      const int k1 = k + kPoolLanes, k2 = k + 2 * kPoolLanes, k3 = k + 3 * kPoolLanes;
+      a0 += __ldg(base + ((size_t)(y0 + k / ww) * W + x0 + k % ww) * pitch);
+      a1 += __ldg(base + ((size_t)(y0 + k1 / ww) * W + x0 + k1 % ww) * pitch);
+      a2 += __ldg(base + ((size_t)(y0 + k2 / ww) * W + x0 + k2 % ww) * pitch);
+      a3 += __ldg(base + ((size_t)(y0 + k3 / ww) * W + x0 + k3 % ww) * pitch);
+    }
+    for (; k < cnt; k += kPoolLanes) a0 += __ldg(base + ((size_t)(y0 + k / ww) * W + x0 + k % ww) * pitch);
   }
-  sv[threadIdx.x] = a;
+  sv[threadIdx.x] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (lane == 0 && c < C) {
-    a += sv[64 + cx] + sv[128 + cx] + sv[192 + cx];
+    float a = 0.f;
+    for (int l = 0; l < kPoolLanes; ++l) a += sv[l * 64 + cx];
     pooled[((size_t)n * gridDim.x + bin) * C + c] = a / (float)cnt;
   }
 }
@@ -175,30 +185,39 @@ psp_up_fwd_kernel(const float* __restrict__ src, int C4, int s, int nb_total, in
   }
 }
 
-// dsrc[n][first_bin + iy*s+ix][c] = sum_{y,x} wy*wx * dout[n][y][x][coff + c]; block per (bin, n, 64 channels), 4 lanes
-__global__ void __launch_bounds__(256)
+// dsrc[n][first_bin + iy*s+ix][c] = sum_{y,x} wy*wx * dout[n][y][x][coff + c]; block per (bin, n, 64 channels), 16 pixel
+// lanes over the bin's support only (rows/cols whose bilinear footprint touches source cell (iy, ix))
+__global__ void __launch_bounds__(64 * kPoolLanes)
 psp_up_bwd_kernel(const float* __restrict__ dout, int pitch, int coff, int C, int s, int nb_total, int first_bin,
                   float* __restrict__ dsrc, int H, int W) {
-  __shared__ float sv[256];
+  __shared__ float sv[64 * kPoolLanes];
   const int bin = blockIdx.x, n = blockIdx.y, cx = threadIdx.x & 63, lane = threadIdx.x >> 6, c = blockIdx.z * 64 + cx;
   const int iy = bin / s, ix = bin - iy * s;
+  const float sy = H > 1 ? (float)(s - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(s - 1) / (float)(W - 1) : 0.f;
+  int ylo = 0, yhi = H - 1, xlo = 0, xhi = W - 1;
+  if (sy > 0.f) { ylo = max(0, (int)floorf((float)(iy - 1) / sy) - 1); yhi = min(H - 1, (int)ceilf((float)(iy + 1) / sy) + 1); }
+  if (sx > 0.f) { xlo = max(0, (int)floorf((float)(ix - 1) / sx) - 1); xhi = min(W - 1, (int)ceilf((float)(ix + 1) / sx) + 1); }
+  const int ww = xhi - xlo + 1, cnt = (yhi - ylo + 1) * ww;
   float a = 0.f;
   if (c < C) {
     const float* base = dout + (size_t)n * H * W * pitch + coff + c;
-    for (int k = lane; k < H * W; k += 4) {
-      const int yy = k / W, xx = k - yy * W;
+    for (int k = lane; k < cnt; k += kPoolLanes) {
+      const int yy = ylo + k / ww, xx = xlo + k % ww;
       const Lin by = lin(yy, s, H);
       float wy = 0.f; if (by.i0 == iy) wy += by.l0; if (by.i1 == iy) wy += by.l1;
-      if (wy == 0.f) continue;
       const Lin bx = lin(xx, s, W);
       float wx = 0.f; if (bx.i0 == ix) wx += bx.l0; if (bx.i1 == ix) wx += bx.l1;
-      if (wx == 0.f) continue;
-      a += wy * wx * __ldg(base + (size_t)k * pitch);
+      const float wgt = wy * wx;
+      if (wgt != 0.f) a += wgt * __ldg(base + ((size_t)yy * W + xx) * pitch);
     }
   }
   sv[threadIdx.x] = a;
   __syncthreads();
-  if (lane == 0 && c < C) dsrc[((size_t)n * nb_total + first_bin + bin) * C + c] = a + sv[64 + cx] + sv[128 + cx] + sv[192 + cx];
+  if (lane == 0 && c < C) {
+    float t = 0.f;
+    for (int l = 0; l < kPoolLanes; ++l) t += sv[l * 64 + cx];
+    dsrc[((size_t)n * nb_total + first_bin + bin) * C + c] = t;
+  }
 }
 
 // strided channel-slice copy: dst[row][doff + c] = src[row][soff + c]
@@ -264,7 +283,7 @@ extern "C" int skd_psp_pool_fwd(int N, int H, int W, int C, const float* x, int 
                                 float* pooled, cudaStream_t st) {
   if (levels < 1 || levels > 4) { set_error_msg("skd_psp_pool_fwd", "1..4 pyramid levels"); return 0; }
   const Pyramid p = make_pyramid(levels, sizes);
-  psp_pool_fwd_kernel<<<dim3(p.first_bin[levels], N, (C + 63) / 64), 256, 0, st>>>(x, x_pitch, C, H, W, p, pooled);
+  psp_pool_fwd_kernel<<<dim3(p.first_bin[levels], N, (C + 63) / 64), 64 * kPoolLanes, 0, st>>>(x, x_pitch, C, H, W, p, pooled);
   return finish("skd_psp_pool_fwd");
 }
 
@@ -286,7 +305,7 @@ extern "C" int skd_psp_upsample_fwd(int N, int H, int W, int C, int s, const flo
 
 extern "C" int skd_psp_upsample_bwd(int N, int H, int W, int C, int s, const float* dout, int dout_pitch, int chan_off,
                                     float* dsrc, int nbins_total, int first_bin, cudaStream_t st) {
-  psp_up_bwd_kernel<<<dim3(s * s, N, (C + 63) / 64), 256, 0, st>>>(dout, dout_pitch, chan_off, C, s, nbins_total, first_bin,
+  psp_up_bwd_kernel<<<dim3(s * s, N, (C + 63) / 64), 64 * kPoolLanes, 0, st>>>(dout, dout_pitch, chan_off, C, s, nbins_total, first_bin,
                                                                   dsrc, H, W);
   return finish("skd_psp_upsample_bwd");
 }

@@ -63,32 +63,71 @@ class DsnCrossEntropy(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------ layers
+def _padded_weight(w_ohwi, cout_p, cin_p):
+    cout, kh, kw, cin = w_ohwi.shape
+    if cout_p == cout and cin_p == cin:
+        return w_ohwi
+    wp = torch.zeros((cout_p, kh, kw, cin_p), device=w_ohwi.device, dtype=torch.float32)
+    wp[:cout, :, :, :cin] = w_ohwi
+    return wp
+
+
+def conv_forward_padded(x, weight, bias, stride, pad, dil, **epi):
+    """tcgen05 forward for any channel count: Cin / Cout that are not multiples of 4 (3-channel image, 19 classes) are
+    zero-padded to the next multiple so that every pixel row is 16-byte aligned for TMA.  Returns a (N,Cout,OH,OW) view."""
+    w = ops.weight_ohwi(weight)
+    cout, kh, kw, cin = w.shape
+    cin_p, cout_p = ops.pad4(cin), ops.pad4(cout)
+    if x.shape[1] != cin_p:                                   # callers may hand in an already padded image
+        x = ops.pad_channels(x, cin_p)
+    wp = _padded_weight(w, cout_p, cin_p)
+    if cout_p != cout:
+        for k in ("scale", "shift"):
+            v = epi.get(k)
+            if v is not None:
+                pv = torch.zeros(cout_p, device=v.device, dtype=torch.float32); pv[:cout] = v; epi[k] = pv
+        if bias is not None:
+            pb = torch.zeros(cout_p, device=bias.device, dtype=torch.float32); pb[:cout] = bias; bias = pb
+    if bias is not None:
+        sc = epi.get("scale")
+        epi["shift"] = bias if epi.get("shift") is None else epi["shift"] + (bias * sc if sc is not None else bias)
+    y = ops.conv2d_fwd(x, wp, stride, pad, dil, **epi)
+    return y[:, :cout] if cout_p != cout else y, x
+
+
 class Conv2d(torch.autograd.Function):
-    """nn.Conv2d forward / dgrad / wgrad on tcgen05 (SIMT direct kernels for the 3-channel stem and strided dgrad).
-    x is NHWC-stored; weight is the (Cout,Cin,KH,KW) parameter held in channels-last (OHWI) storage."""
+    """nn.Conv2d forward / dgrad / wgrad on tcgen05.  x is NHWC-stored; weight is the (Cout,Cin,KH,KW) parameter held in
+    channels-last (OHWI) storage."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad, dil):
-        w = ops.weight_ohwi(weight)
-        y = ops.conv2d_fwd(x, w, stride, pad, dil, shift=bias)
-        ctx.save_for_backward(x, weight)
-        ctx.cfg = (stride, pad, dil, bias is not None)
+        y, xin = conv_forward_padded(x, weight, bias, stride, pad, dil)
+        ctx.save_for_backward(xin, weight)
+        ctx.cfg = (stride, pad, dil, bias is not None, tuple(x.shape))
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
-        stride, pad, dil, has_bias = ctx.cfg
-        dy = ops.to_nhwc(dy)
+        xin, weight = ctx.saved_tensors
+        stride, pad, dil, has_bias, xshape = ctx.cfg
         w = ops.weight_ohwi(weight)
+        cout, kh, kw, cin = w.shape
+        cin_p, cout_p = ops.pad4(cin), ops.pad4(cout)
+        dy = ops.pad_channels(dy, cout_p) if cout_p != cout else ops.to_nhwc(dy)
+        if ops.nhwc_meta(dy)[4] % 4:
+            dy = ops.pad_channels(dy, cout_p)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.conv2d_dgrad(dy, w, x.shape, stride, pad, dil)
+            wp = _padded_weight(w, cout_p, cin_p)
+            dx = ops.conv2d_dgrad(dy, wp, (xshape[0], cin_p, xshape[2], xshape[3]), stride, pad, dil)
+            if cin_p != cin:
+                dx = dx[:, :cin]
         if ctx.needs_input_grad[1]:
-            dw = ops.conv2d_wgrad(x, dy, (w.shape[1], w.shape[2]), stride, pad, dil).permute(0, 3, 1, 2)
+            dw = ops.conv2d_wgrad(xin, dy, (kh, kw), stride, pad, dil)
+            dw = dw[:cout, :, :, :cin].permute(0, 3, 1, 2)
         if has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(dy)
+            db = ops.colsum(dy)[:cout]
         return dx, dw, db, None, None, None
 
 

@@ -21,6 +21,7 @@ import os.path as osp
 import torch
 import torch.distributed as dist
 
+from .. import ops
 from ..optim import FlatSGD
 from ..utils.criterion import (CriterionAdditionalGP, CriterionAdv, CriterionAdvForG, CriterionDSN,
                                CriterionPairWiseforWholeFeatAfterPool, CriterionPixelWise)
@@ -144,9 +145,10 @@ class NetModel():
         return lr
 
     def forward(self):
+        images = ops.pad_channels(self.images, 4)                 # shared by teacher and student
         with torch.no_grad():
-            self.preds_T = self.parallel_teacher.eval()(self.images)
-        self.preds_S = self.parallel_student.train()(self.images)
+            self.preds_T = self.parallel_teacher.eval()(images)
+        self.preds_S = self.parallel_student.train()(images)
 
     def student_backward(self):
         args = self.args

@@ -45,10 +45,9 @@ class Conv2d(nn.Module):
         return Fn.Conv2d.apply(x, self.weight, self.bias, self.stride, self.padding, self.dilation)
 
     def frozen(self, x, scale=None, shift=None, residual=None, act="none", slope=0.0, out=None):
-        if self.bias is not None:
-            shift = self.bias if shift is None else shift + self.bias * scale
-        return ops.conv2d_fwd(x, ops.weight_ohwi(self.weight), self.stride, self.padding, self.dilation, scale=scale,
-                              shift=shift, residual=residual, act=act, slope=slope, out=out)
+        y, _ = Fn.conv_forward_padded(x, self.weight, self.bias, self.stride, self.padding, self.dilation, scale=scale,
+                                      shift=shift, residual=residual, act=act, slope=slope, out=out)
+        return y
 
     def extra_repr(self):
         return '{in_channels}, {out_channels}, kernel_size={kernel_size}, stride={stride}, padding={padding}, dilation={dilation}'.format(**self.__dict__)
@@ -210,7 +209,9 @@ class ResNet(nn.Module):
         return [self.pspmodule.bottleneck[2], self.dsn[2]]
 
     def forward(self, x):
-        x = ops.to_nhwc(x)
+        # the 3-channel image travels as 4 channels (16-byte pixel rows for TMA); a caller that feeds two networks
+        # (NetModel.forward) pads once and passes the 4-channel tensor to both
+        x = ops.pad_channels(x, 4) if x.shape[1] == 3 else ops.to_nhwc(x)
         if not self.training and not torch.is_grad_enabled():
             return self._forward_frozen(x)
         x = self.bn1(self.conv1(x), fuse_relu=True)

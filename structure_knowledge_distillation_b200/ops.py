@@ -36,6 +36,19 @@ def empty_nhwc(n, c, h, w, device, pitch=None):
     return torch.empty((n, h, w, pitch), device=device, dtype=torch.float32).permute(0, 3, 1, 2)[:, :c]
 
 
+def pad4(c):
+    return (c + 3) // 4 * 4
+
+
+def pad_channels(t, cp):
+    """(N,C,H,W) any layout -> dense NHWC tensor with cp >= C channels, zero-filled tail (TMA needs 16-byte pixel rows:
+    the 3-channel image and the 19-class logits are carried as 4 / 20 channels)."""
+    n, c, h, w = t.shape
+    buf = torch.zeros((n, h, w, cp), device=t.device, dtype=torch.float32)
+    buf[..., :c] = t.permute(0, 2, 3, 1)
+    return buf.permute(0, 3, 1, 2)
+
+
 def to_nhwc(t):
     """Any (N,C,H,W) tensor -> channels-last storage (no copy if it already is)."""
     return t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t
@@ -308,7 +321,7 @@ def pixelwise_fwd(S, T):
 
 def pixelwise_bwd(S, T, grad_out):
     n, c, h, w = S.shape
-    dS = torch.empty_like(S)                         # preserves S's memory format
+    dS = torch.empty_strided(S.shape, S.stride(), device=S.device, dtype=torch.float32)   # same layout as S
     lib().skd_pixelwise_bwd(n, c, h * w, _p(S), *pixel_strides(S), _p(T), *pixel_strides(T), _p(dS), *pixel_strides(dS),
                             _p(grad_out), 1.0 / (h * w), _st())
     return dS
@@ -333,11 +346,10 @@ def dsn_ce_bwd(l0, l1, labels, ignore_index, w0, w1, grad_out, count):
     L = lib()
     heads = 2 if l1 is not None else 1
     ws = torch.empty(L.skd_dsn_ce_bwd_workspace_floats(n, c, w, H, heads), device=l0.device, dtype=torch.float32)
-    d0 = torch.empty_like(l0)
-    d1 = torch.empty_like(l1) if l1 is not None else None
+    # gradient tensors share the logits' strides exactly (pitched channel slices included)
+    d0 = torch.empty_strided(l0.shape, l0.stride(), device=l0.device, dtype=torch.float32)
+    d1 = torch.empty_strided(l1.shape, l1.stride(), device=l1.device, dtype=torch.float32) if l1 is not None else None
     s1 = pixel_strides(l1) if l1 is not None else (0, 0, 0)
-    # gradient tensors share the logits' strides (empty_like keeps the memory format)
-    assert pixel_strides(d0) == pixel_strides(l0)
     L.skd_dsn_ce_bwd(n, c, h, w, H, W, _p(l0), *pixel_strides(l0), _p(l1), *s1, _p(labels), ignore_index, w0, w1,
                      _p(grad_out), _p(count), _p(d0), _p(d1), _p(ws), _st())
     return d0, d1
