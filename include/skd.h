@@ -122,6 +122,7 @@ int skd_colsum(long long P, int C, const float* dy, int ldy, float* db, cudaStre
 int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w, float* wt, int round_tf32, cudaStream_t);
 int skd_round_tf32(long long n, const float* src, float* dst, cudaStream_t);
 void skd_set_tf32_tma_type(int use_tfloat32_type);
+void skd_set_conv_im2col(int on);      /* 1 (default): TMA im2col-mode M tiles for k>1 / strided convs; 0: rectangular tiled-mode tiles */
 
 /* ---- E. pooling / resampling / optimiser ---- */
 int skd_pool_out_size_ceil(int in, int k, int s, int p);

@@ -47,6 +47,7 @@ struct ConvArgs {
   int act; float slope; int round_out;
   int vec_ok;
   int tma_store;
+  int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
 };
 
 template <int BLOCK_N>
@@ -106,6 +107,15 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int iy0 = ty * a.BH * a.stride - a.pad, ix0 = tx * a.BW * a.stride - a.pad;
+        // im2col: first output pixel of the tile (n, p, q) -> filter-origin input coordinates
+        int in0 = 0, ip0 = 0, iq0 = 0;
+        if (a.im2col) {
+          const int m0 = mt * kBlockM;
+          in0 = m0 / (a.rOH * a.rOW);
+          const int r2 = m0 - in0 * (a.rOH * a.rOW);
+          ip0 = (r2 / a.rOW) * a.stride - a.pad;
+          iq0 = (r2 % a.rOW) * a.stride - a.pad;
+        }
         for (int tap = 0; tap < taps; ++tap) {
           const int kh = tap / a.KW, kw = tap - kh * a.KW;
           for (int kc = 0; kc < a.k_chunks; ++kc) {
@@ -113,7 +123,10 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             uint8_t* sa = smem + stage * C::kStageBytes;
             uint8_t* sb = sa + kABytes;
             ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-            ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
+            if (a.im2col)
+              ptx::tma_load_im2col_4d(sa, &tmap_x, &full_bar[stage], kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
+            else
+              ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
             ptx::tma_load_3d(sb, &tmap_w, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
@@ -275,6 +288,23 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  return fn;
+}
+int g_conv_im2col = 1;
+
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
@@ -333,6 +363,8 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
 
 }  // namespace
 
+extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
+
 extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                                     const float* x, int ldx, const float* w, float* y, int ldy, const float* scale,
                                     const float* shift, const float* residual, int ldr, int act, float slope,
@@ -345,10 +377,23 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
   const int OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
   if (OH <= 0 || OW <= 0 || N <= 0) return 1;
   ConvArgs a;
-  a.N = N; a.OH = OH; a.OW = OW; a.Cout = Cout; a.Cin = Cin; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.dil = dil;
-  pick_rect(OH, OW, stride, &a.BH, &a.BW);
-  a.tiles_x = (OW + a.BW - 1) / a.BW; a.tiles_y = (OH + a.BH - 1) / a.BH;
-  a.m_tiles = N * a.tiles_x * a.tiles_y;
+  a.Cout = Cout; a.Cin = Cin; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.dil = dil;
+  a.rOH = OH; a.rOW = OW; a.im2col = 0;
+  // tile geometry of the M (pixel) dimension:
+  //   flat   : 1x1/stride-1 convolutions are plain GEMMs over the [N*H*W][C] matrix -> tiles of 128 consecutive pixels;
+  //   im2col : TMA im2col mode walks 128 consecutive OUTPUT pixels across rows and images (halo = hardware zero fill);
+  //   rect   : BH x BW rectangles of one image through the tiled TMA mode (ragged edges waste up to ~19% at 65x129).
+  const bool flat = (KH == 1 && KW == 1 && stride == 1 && pad == 0);
+  const long long P = (long long)N * OH * OW;
+  const int up_h = pad - (KH - 1) * dil, up_w = pad - (KW - 1) * dil;
+  const bool can_im2col = !flat && g_conv_im2col && get_encode_im2col() && pad <= 128 && up_h >= -128 && up_w >= -128 && stride <= 8 &&
+                          P < (1LL << 31) && (KH - 1) * dil < 65536;
+  int vN = N, vH = H, vW = W;                                // geometry of the tiled-mode input view
+  if (flat) { vN = 1; vH = 1; vW = (int)P; a.N = 1; a.OH = 1; a.OW = (int)P; a.BH = 1; a.BW = 128; }
+  else if (can_im2col) { a.im2col = 1; a.N = 1; a.OH = 1; a.OW = (int)P; a.BH = 1; a.BW = 128; }
+  else { a.N = N; a.OH = OH; a.OW = OW; pick_rect(OH, OW, stride, &a.BH, &a.BW); }
+  a.tiles_x = (a.OW + a.BW - 1) / a.BW; a.tiles_y = (a.OH + a.BH - 1) / a.BH;
+  a.m_tiles = a.N * a.tiles_x * a.tiles_y;
   a.k_chunks = (Cin + kBlockK - 1) / kBlockK;
   a.y = y; a.ldy = ldy; a.scale = scale; a.shift = shift; a.residual = residual; a.ldr = ldr;
   a.act = act; a.slope = slope; a.round_out = round_tf32;
@@ -358,9 +403,20 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
   a.n_tiles = (Cout + bn - 1) / bn;
 
   CUtensorMap tx, tw;
-  {
+  if (a.im2col) {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+    int lower[2] = {-pad, -pad};                             // (W, H): filter origin of the first output pixel
+    int upper[2] = {up_w, up_h};                             // last filter origin = dim-1 + upper
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = get_encode_im2col()(&tx, g_tf32_tma_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                     const_cast<float*>(x), dims, strides, lower, upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeIm2col failed"); return 0; }
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)vW, (cuuint64_t)vH, (cuuint64_t)vN};
+    cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)vW * ldx * 4, (cuuint64_t)vH * vW * ldx * 4};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(a.BW * stride), (cuuint32_t)(a.BH * stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     if (!encode(&tx, 4, x, dims, strides, box, estr, who)) return 0;
@@ -375,8 +431,8 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
   CUtensorMap ty = tx;
   a.tma_store = (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15);
   if (a.tma_store) {
-    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)OW * ldy * 4, (cuuint64_t)OH * OW * ldy * 4};
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)a.OW * ldy * 4, (cuuint64_t)a.OH * a.OW * ldy * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode(&ty, 4, y, dims, strides, box, estr, who, true)) return 0;

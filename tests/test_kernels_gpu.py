@@ -208,6 +208,8 @@ def _tf32_trunc(t):
 
 
 CONV_CASES = [
+    (3, 64, 7, 9, 64, 3, 1, 1, 1),             # tiles that span several images (im2col wrap-around)
+    (2, 32, 65, 129, 32, 3, 1, 4, 4),
     # N, Cin, H, W, Cout, k, stride, pad, dil
     (1, 32, 8, 16, 32, 1, 1, 0, 1),
     (2, 64, 9, 13, 64, 3, 1, 1, 1),
@@ -230,12 +232,16 @@ def test_conv_fwd_tcgen05(ops, case):
     w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5
     ref = _conv_ref64(x, w, s, p, d)
     xc = ops.to_nhwc(x); wo = ops.weight_ohwi(w)
-    y = ops.conv2d_fwd(xc, wo, s, p, d)
     yd = ops.conv2d_fwd(xc, wo, s, p, d, force_direct=True)
-    torch.cuda.synchronize()
-    assert y.shape == ref.shape
     assert rel(yd, ref) < 1e-5, "direct SIMT conv"
-    assert rel(y, ref) < 2e-3, ("tcgen05 TF32 conv", rel(y, ref))          # TF32 operands, fp32 accumulate
+    from structure_knowledge_distillation_b200._cabi import lib
+    for im2col in (0, 1):                                   # rectangular tiled-mode tiles vs TMA im2col-mode tiles
+        lib().skd_set_conv_im2col(im2col)
+        y = ops.conv2d_fwd(xc, wo, s, p, d)
+        torch.cuda.synchronize()
+        assert y.shape == ref.shape
+        assert rel(y, ref) < 2e-3, ("tcgen05 TF32 conv", im2col, rel(y, ref))          # TF32 operands, fp32 accumulate
+    lib().skd_set_conv_im2col(1)
 
 
 def test_conv_fwd_epilogue_and_pitch(ops):
