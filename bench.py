@@ -218,8 +218,15 @@ def run_ours(args, rank, local_rank, world):
         return
     peaks = _peaks()
     tf32_peak = peaks["bf16_sus"] / 2.0                            # kind::tf32 issues at half the bf16 rate
-    conv_ms = sum(s.elapsed_time(e) for s, e, _ in conv_log)
-    conv_flop = sum(f for _, _, f in conv_log)
+    conv_ms = sum(r[0].elapsed_time(r[1]) for r in conv_log)
+    conv_flop = sum(r[2] for r in conv_log)
+    if args.conv_table:
+        import collections
+        agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+        for r in conv_log:
+            a = agg[r[3]]; a[0] += 1; a[1] += r[0].elapsed_time(r[1]); a[2] += r[2]
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+            print("CONV %-48s n=%3d  %7.3f ms/step  %6.0f TF" % (k, v[0] // args.steps, v[1] / args.steps, v[2] / v[1] / 1e9), file=sys.stderr)
     achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_fwd_traffic.json")
@@ -255,6 +262,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-table", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

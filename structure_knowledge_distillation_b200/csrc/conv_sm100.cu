@@ -200,6 +200,21 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       for (int ch = group; ch < BLOCK_N / 32; ch += 2) {
         const int c0 = nt * BLOCK_N + ch * 32;
         if (c0 >= a.Cout) break;                                               // CTA-uniform
+        // residual tile read COALESCED (8 threads cover the 128 B of one pixel row, a warp covers 4 rows; the per-row
+        // mapping of the TMEM load would touch 32 lines per instruction), issued before the TMEM load to overlap its latency
+        const bool coalesced_res = (a.residual != nullptr) && a.tma_store && a.vec_ok;      // CTA-uniform
+        float4 q[8];
+        const int gt = (ew & 3) * 32 + lane, ck = gt & 7;
+        if (coalesced_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 16 + (gt >> 3);
+            const int roy = ty * a.BH + rr / a.BW, rox = tx * a.BW + rr % a.BW;
+            q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (roy < a.OH && rox < a.OW && c0 + ck * 4 + 3 < a.Cout)
+              q[i] = __ldg(reinterpret_cast<const float4*>(a.residual + (((size_t)img * a.OH + roy) * a.OW + rox) * a.ldr + c0 + ck * 4));
+          }
+        }
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + ch * 32, r);
         ptx::tmem_ld_wait();
@@ -214,31 +229,25 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z);
           v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
         }
-        if (rrow) {
-          if (a.vec_ok && c0 + 32 <= a.Cout) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(rrow + c0) + j);
-              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
-            }
-          } else {
+        if (!coalesced_res) {
+          if (rrow) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (c0 + j < a.Cout) v[j] += __ldg(rrow + c0 + j);
           }
-        }
-        if (a.act == ACT_RELU) {
+          if (a.act == ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (a.act == ACT_LEAKY) {
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (a.act == ACT_LEAKY) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] < 0.f ? v[j] * a.slope : v[j];
-        } else if (a.act == ACT_ELU) {
+            for (int j = 0; j < 32; ++j) v[j] = v[j] < 0.f ? v[j] * a.slope : v[j];
+          } else if (a.act == ACT_ELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] < 0.f ? expm1f(v[j]) : v[j];
-        }
-        if (a.round_out) {
+            for (int j = 0; j < 32; ++j) v[j] = v[j] < 0.f ? expm1f(v[j]) : v[j];
+          }
+          if (a.round_out) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
+          }
         }
         if (a.tma_store) {
           // stage the chunk in shared memory (128B-swizzled rows) and let the TMA engine write the BH x BW x 32 box:
@@ -249,6 +258,24 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (coalesced_res) {
+            // residual add + activation on the staged tile (residual registers were loaded coalesced above)
+            ptx::named_bar_sync(1 + group, 128);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 16 + (gt >> 3);
+              float4* sp = reinterpret_cast<float4*>(stg + rr * 128 + ((ck ^ (rr & 7)) << 4));
+              float4 o = *sp;
+              o.x += q[i].x; o.y += q[i].y; o.z += q[i].z; o.w += q[i].w;
+              if (a.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              else if (a.act == ACT_LEAKY) {
+                o.x = o.x < 0.f ? o.x * a.slope : o.x; o.y = o.y < 0.f ? o.y * a.slope : o.y;
+                o.z = o.z < 0.f ? o.z * a.slope : o.z; o.w = o.w < 0.f ? o.w * a.slope : o.w;
+              }
+              if (a.round_out) { o.x = ptx::round_tf32(o.x); o.y = ptx::round_tf32(o.y); o.z = ptx::round_tf32(o.z); o.w = ptx::round_tf32(o.w); }
+              *sp = o;
+            }
+          }
           ptx::fence_proxy_async();
           ptx::named_bar_sync(1 + group, 128);
           if (is_store_leader) {

@@ -186,7 +186,7 @@ def conv2d_fwd(x, w_ohwi, stride, pad, dil, scale=None, shift=None, residual=Non
                            _p(shift), _p(residual), ldr, ACT[act], slope, int(round_tf32), _st())
     if log is not None:
         ev1.record()
-        log.append((ev0, ev1, 2.0 * n * oh * ow * cout * cin * kh * kw))
+        log.append((ev0, ev1, 2.0 * n * oh * ow * cout * cin * kh * kw, ("fwd", n, cin, h, w, cout, kh, stride, dil)))
     return out
 
 
@@ -208,7 +208,7 @@ def conv2d_dgrad(dy, w_ohwi, x_shape, stride, pad, dil, round_tf32=False, force_
                                None, None, None, 0, 0, 0.0, int(round_tf32), _st())
         if log is not None:
             ev1.record()
-            log.append((ev0, ev1, 2.0 * n * h * w * cin * cout * kh * kw))
+            log.append((ev0, ev1, 2.0 * n * h * w * cin * cout * kh * kw, ("dgrad", n, cout, doh, dow, cin, kh, 1, dil)))
     else:
         L.skd_conv2d_dgrad_direct(n, h, w, cin, cout, kh, kw, stride, pad, dil, _p(dy), ldy, _p(w_ohwi), _p(dx), cin, _st())
     return dx
