@@ -94,6 +94,9 @@ class NetModel():
             self.criterion_AdditionalGP = CriterionAdditionalGP(self.parallel_D, args.lambda_gp)
         self.criterion_adv_for_G = CriterionAdvForG(args.adv_loss_type)
 
+        self._graphs = None
+        if _arg(args, "cuda_graph", False):
+            self.enable_cuda_graphs()
         self.mc_G_loss = 0.0
         self.pi_G_loss = 0.0
         self.pa_G_loss = 0.0
@@ -133,6 +136,11 @@ class NetModel():
     # ---- the reference's step API ------------------------------------------------------------------------
     def set_input(self, data):
         images, labels = data[0], data[1]
+        if self._graphs is not None and self._graphs.get("captured"):
+            # replayed CUDA graphs read fixed device buffers: copy the new batch into them
+            self.images.copy_(images, non_blocking=True)
+            self.labels.copy_(labels, non_blocking=True)
+            return
         self.images = images.to(self.device, non_blocking=True)
         self.labels = labels.long().to(self.device, non_blocking=True)
 
@@ -182,14 +190,75 @@ class NetModel():
         self.D_solver.all_reduce_grads(self.world)
         self.D_solver.step()
 
-    def optimize_parameters(self):
+    def _student_phase(self):
         self.forward()
         self.G_solver.zero_grad()
         self.student_backward()
+
+    def _discriminator_phase(self):
+        """discriminator_backward() without the optimizer step (kd_model.py:153-163)."""
+        self.D_solver.zero_grad()
+        args = self.args
+        d_out_T = self.parallel_D(self.preds_T[0].detach())
+        d_out_S = self.parallel_D(self.preds_S[0].detach())
+        d_loss = args.lambda_d * self.criterion_adv(d_out_S, d_out_T)
+        if args.adv_loss_type == 'wgan-gp':
+            d_loss = d_loss + args.lambda_d * self.criterion_AdditionalGP(self.preds_S, self.preds_T)
+        d_loss.backward()
+        self.D_loss = _LazyScalar(d_loss)
+
+    def optimize_parameters(self):
+        if self._graphs is not None:
+            return self._optimize_graphed()
+        self._student_phase()
         self.G_solver.all_reduce_grads(self.world)       # the one collective of the path (teacher is frozen)
         self.G_solver.step()
         if self.args.ho == True:
             self.discriminator_backward()
+
+    # ---- CUDA-graph execution: the ~4 000 launches of a step are captured once and replayed ------------------------
+    def enable_cuda_graphs(self, warmup=3):
+        """Capture the student phase (teacher fwd, student fwd, losses, backward) and the discriminator phase as two CUDA
+        graphs after `warmup` eager steps; the NCCL all-reduce and the two fused SGD kernels stay eager between them
+        (the learning rate is a device scalar, so poly-LR updates need no re-capture)."""
+        self._graphs = dict(calls=0, warmup=warmup, captured=False)
+
+    def _optimize_graphed(self):
+        g = self._graphs
+        if not g["captured"]:
+            g["calls"] += 1
+            if g["calls"] <= g["warmup"]:
+                # eager warm-up on a side stream (torch's CUDA-graph recipe): autograd's gradient accumulators must not be
+                # bound to the legacy default stream, which cannot take part in a capture
+                side = g.setdefault("side", torch.cuda.Stream())
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._student_phase()
+                    self.G_solver.all_reduce_grads(self.world); self.G_solver.step()
+                    if self.args.ho == True:
+                        self._discriminator_phase()
+                        self.D_solver.all_reduce_grads(self.world); self.D_solver.step()
+                torch.cuda.current_stream().wait_stream(side)
+                return
+            # static input buffers + capture
+            self.images = self.images.clone(); self.labels = self.labels.clone()
+            torch.cuda.synchronize()
+            g["student"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g["student"]):
+                self._student_phase()
+            self.G_solver.all_reduce_grads(self.world); self.G_solver.step()
+            if self.args.ho == True:
+                g["D"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g["D"], pool=g["student"].pool()):
+                    self._discriminator_phase()
+                self.D_solver.all_reduce_grads(self.world); self.D_solver.step()
+            g["captured"] = True
+            return
+        g["student"].replay()
+        self.G_solver.all_reduce_grads(self.world); self.G_solver.step()
+        if self.args.ho == True:
+            g["D"].replay()
+            self.D_solver.all_reduce_grads(self.world); self.D_solver.step()
 
     def evalute_model(self, model, loader, gpu_id, input_size, num_classes, whole):
         raise NotImplementedError("evaluation (networks/evaluate.py) is outside the distillation hot path; see DESIGN.md")

@@ -30,11 +30,14 @@ class SpectralNorm(nn.Module):
         u, v, w = getattr(m, n + "_u"), getattr(m, n + "_v"), getattr(m, n + "_bar")
         w2 = w.view(w.shape[0], -1)
         with torch.no_grad():
+            nu, nv = u, v
             for _ in range(self.power_iterations):
-                nv = l2normalize(torch.mv(w2.t(), u))
+                nv = l2normalize(torch.mv(w2.t(), nu))
                 nu = l2normalize(torch.mv(w2, nv))
-                v.data, u.data = nv, nu
-        sigma = u.dot(w2.mv(v))
+            # persistent state advances in place (CUDA-graph safe); autograd saves the fresh nu/nv, so several forwards
+            # before one backward (kd_model.py:156-161) do not trip the version counter
+            v.copy_(nv); u.copy_(nu)
+        sigma = nu.dot(w2.mv(nv))
         setattr(m, n, w / sigma.expand_as(w))
 
     def forward(self, *args):

@@ -70,8 +70,8 @@ class FlatSGD:
     def step(self):
         g = self.param_groups[0]
         self.lr_dev.fill_(float(g['lr']))
-        ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.lr_dev, g['momentum'], g['weight_decay'], self.steps == 0,
-                     self.grad_scale)
+        # momentum buffer starts at zero, so the first step needs no special case (v = mu*0 + d)
+        ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.lr_dev, g['momentum'], g['weight_decay'], False, self.grad_scale)
         self.steps += 1
 
     def state_dict(self):
