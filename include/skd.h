@@ -105,6 +105,11 @@ int skd_pairwise_bwd(int N, int nodes, int CS, const float* E, const float* pool
 int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
                          int ldx, const float* w, float* y, int ldy, const float* scale, const float* shift,
                          const float* residual, int ldr, int act, float slope, int round_tf32, cudaStream_t);
+/* same kernel, output written through explicit element strides y[n*y_img + oy*y_row + ox*y_pix + c] (every-other-pixel sub-grids:
+   the data gradient of a stride-2 convolution is 4 stride-1 convolutions of dy, one per input-pixel parity class) */
+int skd_conv2d_fwd_sm100_strided(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                                 int ldx, const float* w, float* y, long long y_pix, long long y_row, long long y_img, int out_h, int out_w,
+                                 int round_tf32, cudaStream_t);   /* out_h/out_w > 0 override the output extent (far-end zero padding) */
 /* tcgen05 weight gradient: dw[Cout][KH][KW][Cin] = sum_pixels dy[p][co] * x[p+tap][ci]; workspace from the size query */
 long long skd_conv2d_wgrad_sm100_workspace_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil);
 int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
@@ -122,6 +127,7 @@ int skd_colsum(long long P, int C, const float* dy, int ldy, float* db, cudaStre
 int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w, float* wt, int round_tf32, cudaStream_t);
 int skd_round_tf32(long long n, const float* src, float* dst, cudaStream_t);
 void skd_set_tf32_tma_type(int use_tfloat32_type);
+void skd_set_wgrad_linear(int on);     /* 1 (default): wgrad K-blocks are 32 consecutive pixels (im2col TMA); 0: 4x8 rectangles */
 void skd_set_conv_im2col(int on);      /* 1 (default): TMA im2col-mode M tiles for k>1 / strided convs; 0: rectangular tiled-mode tiles */
 
 /* ---- E. pooling / resampling / optimiser ---- */

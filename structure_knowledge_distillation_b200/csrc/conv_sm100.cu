@@ -392,16 +392,18 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
 
 extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
 
-extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
-                                    const float* x, int ldx, const float* w, float* y, int ldy, const float* scale,
-                                    const float* shift, const float* residual, int ldr, int act, float slope,
-                                    int round_tf32, cudaStream_t st) {
+static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                         const float* x, int ldx, const float* w, float* y, int ldy, long long y_row, long long y_img, int oh_req,
+                         int ow_req, const float* scale, const float* shift, const float* residual, int ldr, int act, float slope,
+                         int round_tf32, cudaStream_t st) {
   const char* who = "skd_conv2d_fwd_sm100";
   if (Cin % 4 || ldx % 4 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
     set_error_msg(who, "Cin and the input pitch must be multiples of 4 floats and pointers 16-byte aligned (TMA)");
     return 0;
   }
-  const int OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+  // oh_req/ow_req > 0: caller-chosen output extent (rows/cols past the natural size read zero-filled input: far-end padding)
+  const int OH = oh_req > 0 ? oh_req : (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+  const int OW = ow_req > 0 ? ow_req : (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
   if (OH <= 0 || OW <= 0 || N <= 0) return 1;
   ConvArgs a;
   a.Cout = Cout; a.Cin = Cin; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.dil = dil;
@@ -410,10 +412,13 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
   //   flat   : 1x1/stride-1 convolutions are plain GEMMs over the [N*H*W][C] matrix -> tiles of 128 consecutive pixels;
   //   im2col : TMA im2col mode walks 128 consecutive OUTPUT pixels across rows and images (halo = hardware zero fill);
   //   rect   : BH x BW rectangles of one image through the tiled TMA mode (ragged edges waste up to ~19% at 65x129).
-  const bool flat = (KH == 1 && KW == 1 && stride == 1 && pad == 0);
+  // output addressed as y[n*y_img + oy*y_row + ox*ldy + c]; anything but the dense NHWC strides (e.g. an every-other-pixel
+  // sub-grid written by the strided data-gradient) forces rectangular tiles + TMA store
+  const bool strided_out = (y_row != (long long)OW * ldy) || (y_img != (long long)OH * y_row);
+  const bool flat = !strided_out && (KH == 1 && KW == 1 && stride == 1 && pad == 0);
   const long long P = (long long)N * OH * OW;
   const int up_h = pad - (KH - 1) * dil, up_w = pad - (KW - 1) * dil;
-  const bool can_im2col = !flat && g_conv_im2col && get_encode_im2col() && pad <= 128 && up_h >= -128 && up_w >= -128 && stride <= 8 &&
+  const bool can_im2col = !flat && !strided_out && g_conv_im2col && get_encode_im2col() && pad <= 128 && up_h >= -128 && up_w >= -128 && stride <= 8 &&
                           P < (1LL << 31) && (KH - 1) * dil < 65536;
   int vN = N, vH = H, vW = W;                                // geometry of the tiled-mode input view
   if (flat) { vN = 1; vH = 1; vW = (int)P; a.N = 1; a.OH = 1; a.OW = (int)P; a.BH = 1; a.BW = 128; }
@@ -456,10 +461,12 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
     if (!encode(&tw, 3, w, dims, strides, box, estr, who)) return 0;
   }
   CUtensorMap ty = tx;
-  a.tma_store = (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15);
+  a.tma_store = (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) && (y_row % 4 == 0) && (y_img % 4 == 0);
+  if (strided_out && (!a.tma_store || residual)) { set_error_msg(who, "strided output needs 16-byte aligned strides and no residual"); return 0; }
   if (a.tma_store) {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)a.N};
     cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)a.OW * ldy * 4, (cuuint64_t)a.OH * a.OW * ldy * 4};
+    if (strided_out) { strides[1] = (cuuint64_t)y_row * 4; strides[2] = (cuuint64_t)y_img * 4; }
     cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode(&ty, 4, y, dims, strides, box, estr, who, true)) return 0;
@@ -470,4 +477,20 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
     case 64: return launch<64>(tx, tw, ty, a, st);
     default: return launch<32>(tx, tw, ty, a, st);
   }
+}
+
+extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                    const float* x, int ldx, const float* w, float* y, int ldy, const float* scale,
+                                    const float* shift, const float* residual, int ldr, int act, float slope,
+                                    int round_tf32, cudaStream_t st) {
+  const int OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, ldx, w, y, ldy, (long long)OW * ldy, (long long)OH * OW * ldy, 0, 0,
+                       scale, shift, residual, ldr, act, slope, round_tf32, st);
+}
+
+extern "C" int skd_conv2d_fwd_sm100_strided(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                            const float* x, int ldx, const float* w, float* y, long long y_pix, long long y_row,
+                                            long long y_img, int out_h, int out_w, int round_tf32, cudaStream_t st) {
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, ldx, w, y, (int)y_pix, y_row, y_img, out_h, out_w, nullptr, nullptr, nullptr, 0,
+                       0, 0.f, round_tf32, st);
 }

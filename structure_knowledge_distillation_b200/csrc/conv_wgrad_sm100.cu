@@ -28,6 +28,7 @@ struct WgArgs {
   int BHk, BWk, kb_x, kb_y;                // pixel K-blocks per image
   int m_tiles, n_tiles, taps, splits, kb_total, kb_per_split;
   float* ws;                               // [splits][Cout][taps*Cin]
+  int linear;                              // K-blocks are 32 consecutive output pixels (dY as a [P][Cout] matrix, X through TMA im2col)
 };
 
 template <int BLOCK_N>
@@ -80,20 +81,33 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
         const int kb0 = split * a.kb_per_split;
         const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          const int img = kb / kb_per_img, q = kb - img * kb_per_img;
-          const int by = q / a.kb_x, bx = q - by * a.kb_x;
-          const int oy0 = by * a.BHk, ox0 = bx * a.BWk;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
           ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (a.linear) {
+            const int p0 = kb * kKPix;
+            const int img = p0 / (a.OH * a.OW), r2 = p0 - img * (a.OH * a.OW);
+            const int oy = r2 / a.OW, ox = r2 - oy * a.OW;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            ptx::tma_load_4d(sa + c * kChunkBytes, &tmap_dy, &full_bar[stage], mt * kBlockM + c * 32, ox0, oy0, img);
+            for (int c = 0; c < 4; ++c)
+              ptx::tma_load_4d(sa + c * kChunkBytes, &tmap_dy, &full_bar[stage], mt * kBlockM + c * 32, p0, 0, 0);
 #pragma unroll
-          for (int c = 0; c < BLOCK_N / 32; ++c)
-            ptx::tma_load_4d(sb + c * kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32,
-                             ox0 * a.stride - a.pad + kw * a.dil, oy0 * a.stride - a.pad + kh * a.dil, img);
+            for (int c = 0; c < BLOCK_N / 32; ++c)
+              ptx::tma_load_im2col_4d(sb + c * kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32, ox * a.stride - a.pad,
+                                      oy * a.stride - a.pad, img, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
+          } else {
+            const int img = kb / kb_per_img, q = kb - img * kb_per_img;
+            const int by = q / a.kb_x, bx = q - by * a.kb_x;
+            const int oy0 = by * a.BHk, ox0 = bx * a.BWk;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              ptx::tma_load_4d(sa + c * kChunkBytes, &tmap_dy, &full_bar[stage], mt * kBlockM + c * 32, ox0, oy0, img);
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 32; ++c)
+              ptx::tma_load_4d(sb + c * kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32,
+                               ox0 * a.stride - a.pad + kw * a.dil, oy0 * a.stride - a.pad + kh * a.dil, img);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -201,7 +215,9 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-struct Plan { int OH, OW, BHk, BWk, kb_x, kb_y, kb_total, bn, m_tiles, n_tiles, taps, splits, kb_per_split; };
+struct Plan { int OH, OW, BHk, BWk, kb_x, kb_y, kb_total, bn, m_tiles, n_tiles, taps, splits, kb_per_split, linear; };
+
+int g_wgrad_linear = 1;
 
 Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil) {
   Plan p;
@@ -214,6 +230,9 @@ Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int strid
   }
   p.kb_x = (p.OW + p.BWk - 1) / p.BWk; p.kb_y = (p.OH + p.BHk - 1) / p.BHk;
   p.kb_total = N * p.kb_x * p.kb_y;
+  const int up_h = pad - (KH - 1) * dil, up_w = pad - (KW - 1) * dil;
+  p.linear = g_wgrad_linear && pad <= 128 && up_h >= -128 && up_w >= -128 && stride <= 8 && (long long)N * p.OH * p.OW < (1LL << 31);
+  if (p.linear) p.kb_total = (int)(((long long)N * p.OH * p.OW + kKPix - 1) / kKPix);
   p.bn = Cin > 128 ? 256 : (Cin > 64 ? 128 : (Cin > 32 ? 64 : 32));
   p.m_tiles = (Cout + kBlockM - 1) / kBlockM; p.n_tiles = (Cin + p.bn - 1) / p.bn; p.taps = KH * KW;
   const int tiles = p.m_tiles * p.n_tiles * p.taps;
@@ -242,6 +261,8 @@ int launch(const CUtensorMap& tdy, const CUtensorMap& tx, const WgArgs& a, int u
 
 }  // namespace
 
+extern "C" void skd_set_wgrad_linear(int on) { g_wgrad_linear = on ? 1 : 0; }
+
 extern "C" long long skd_conv2d_wgrad_sm100_workspace_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
                                                              int pad, int dil) {
   const Plan p = make_plan(N, H, W, Cin, Cout, KH, KW, stride, pad, dil);
@@ -263,6 +284,39 @@ extern "C" int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, in
   if (!enc) { set_error_msg(who, "cuTensorMapEncodeTiled unavailable (no CUDA driver)"); return 0; }
   const CUtensorMapDataType dt = skd::g_tf32_tma_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUtensorMap tdy, tx;
+  if (p.linear) {
+    typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                       const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeIm2colFn enc_i2c = nullptr;
+    if (!enc_i2c) {
+      void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        enc_i2c = reinterpret_cast<EncodeIm2colFn>(fp);
+    }
+    if (!enc_i2c) { set_error_msg(who, "cuTensorMapEncodeIm2col unavailable"); return 0; }
+    const long long P = (long long)N * p.OH * p.OW;
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)P, 1, 1};
+      cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)P * ldy * 4, (cuuint64_t)P * ldy * 4};
+      cuuint32_t box[4] = {32, (cuuint32_t)kKPix, 1, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = enc(&tdy, dt, 4, const_cast<float*>(dy), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeTiled(dy, linear) failed"); return 0; }
+    }
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+      int lower[2] = {-pad, -pad};
+      int upper[2] = {pad - (KW - 1) * dil, pad - (KH - 1) * dil};
+      cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+      CUresult r = enc_i2c(&tx, dt, 4, const_cast<float*>(x), dims, strides, lower, upper, 32, (cuuint32_t)kKPix, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeIm2col(x) failed"); return 0; }
+    }
+  } else {
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)p.OW * ldy * 4, (cuuint64_t)p.OH * p.OW * ldy * 4};
@@ -281,11 +335,13 @@ extern "C" int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, in
                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeTiled(x) failed"); return 0; }
   }
+  }
   WgArgs a;
   a.N = N; a.OH = p.OH; a.OW = p.OW; a.Cout = Cout; a.Cin = Cin; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.dil = dil;
   a.BHk = p.BHk; a.BWk = p.BWk; a.kb_x = p.kb_x; a.kb_y = p.kb_y; a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.taps = p.taps;
   a.splits = p.splits; a.kb_total = p.kb_total; a.kb_per_split = p.kb_per_split;
   a.ws = p.splits == 1 ? dw : workspace;
+  a.linear = p.linear;
   const int units = p.m_tiles * p.n_tiles * p.taps * p.splits;
   int ok;
   switch (p.bn) {

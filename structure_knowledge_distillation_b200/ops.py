@@ -209,6 +209,31 @@ def conv2d_dgrad(dy, w_ohwi, x_shape, stride, pad, dil, round_tf32=False, force_
         if log is not None:
             ev1.record()
             log.append((ev0, ev1, 2.0 * n * h * w * cin * cout * kh * kw, ("dgrad", n, cout, doh, dow, cin, kh, 1, dil)))
+    elif stride == 2 and dil == 1 and not force_direct and cout % 4 == 0 and ldy % 4 == 0 and cin % 4 == 0:
+        # dgrad of a stride-2 convolution = one stride-1 convolution of dy per input-pixel parity class (py, px): the taps
+        # with (py + pad - kh) even, taken in descending kh order, written to the every-other-pixel sub-grid of dx
+        dx.zero_()                                           # classes without a tap (1x1 stride-2: odd rows/cols) stay zero
+        for py in range(2):
+            khs = [k for k in range(kh) if (py + pad - k) % 2 == 0]
+            if not khs or py >= h:
+                continue
+            for px in range(2):
+                kws = [k for k in range(kw) if (px + pad - k) % 2 == 0]
+                if not kws or px >= w:
+                    continue
+                ty, tx = [(py + pad - k) // 2 for k in khs], [(px + pad - k) // 2 for k in kws]
+                khs_d, kws_d = khs[::-1], kws[::-1]          # ascending offset t <-> descending tap index
+                pad_y, pad_x = -min(ty), -min(tx)
+                assert pad_y == pad_x, "asymmetric sub-kernel padding is not supported"
+                wsub = torch.stack([w_ohwi[:, a] for a in khs_d], 1)               # device-side gathers only (graph capturable)
+                wsub = torch.stack([wsub[:, :, b] for b in kws_d], 2)              # [Cout][KH'][KW'][Cin]
+                wt = wsub.permute(3, 1, 2, 0).contiguous()   # [Cin][KH'][KW'][Cout]
+                hc, wc = (h - py + 1) // 2, (w - px + 1) // 2
+                view = dx[:, :, py::2, px::2]
+                # output extent = size of the parity class; taps that fall past dy's edge read hardware zero fill
+                L.skd_conv2d_fwd_sm100_strided(n, doh, dow, cout, cin, len(khs), len(kws), 1, pad_y, 1, _p(dy), ldy, _p(wt),
+                                               view.data_ptr(), view.stride(3), view.stride(2), view.stride(0), hc, wc,
+                                               int(round_tf32), _st())
     else:
         L.skd_conv2d_dgrad_direct(n, h, w, cin, cout, kh, kw, stride, pad, dil, _p(dy), ldy, _p(w_ohwi), _p(dx), cin, _st())
     return dx

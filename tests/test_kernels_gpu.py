@@ -262,6 +262,7 @@ def test_conv_fwd_epilogue_and_pitch(ops):
 
 
 @pytest.mark.parametrize("case", [(2, 64, 9, 13, 64, 3, 1, 1, 1), (1, 128, 17, 19, 256, 3, 1, 2, 2), (2, 64, 33, 31, 128, 3, 2, 1, 1),
+                                  (2, 64, 129, 257, 128, 3, 2, 1, 1), (1, 64, 34, 32, 64, 3, 2, 1, 1),
                                   (2, 128, 33, 31, 256, 1, 2, 0, 1), (1, 256, 12, 9, 512, 3, 1, 4, 4), (1, 512, 9, 9, 128, 1, 1, 0, 1),
                                   (2, 64, 65, 129, 64, 3, 1, 1, 1)])
 def test_conv_backward(ops, case):
@@ -276,9 +277,13 @@ def test_conv_backward(ops, case):
     dw_ref = w.grad.permute(0, 2, 3, 1)
     assert rel(ops.conv2d_wgrad(xc, dyc, (k, k), s, p, d, force_direct=True), dw_ref) < 1e-4, "direct wgrad"
     assert rel(ops.conv2d_dgrad(dyc, wo, x.shape, s, p, d, force_direct=True), x.grad) < 1e-5, "direct dgrad"
-    assert rel(ops.conv2d_wgrad(xc, dyc, (k, k), s, p, d), dw_ref) < 2e-3, "tcgen05 wgrad"
-    if s == 1:
-        assert rel(ops.conv2d_dgrad(dyc, wo, x.shape, s, p, d), x.grad) < 2e-3, "tcgen05 dgrad"
+    from structure_knowledge_distillation_b200._cabi import lib
+    for linear in (0, 1):                                   # 4x8 pixel rectangles vs 32 consecutive pixels (im2col TMA) per K block
+        lib().skd_set_wgrad_linear(linear)
+        assert rel(ops.conv2d_wgrad(xc, dyc, (k, k), s, p, d), dw_ref) < 2e-3, ("tcgen05 wgrad", linear)
+    lib().skd_set_wgrad_linear(1)
+    # stride 1: forward kernel on dy with flipped weights; stride 2: one stride-1 conv per input-pixel parity class
+    assert rel(ops.conv2d_dgrad(dyc, wo, x.shape, s, p, d), x.grad) < 2e-3, "tcgen05 dgrad"
 
 
 # ---------------------------------------------------------------------------------------------- pools
