@@ -128,18 +128,22 @@ int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w,
 int skd_round_tf32(long long n, const float* src, float* dst, cudaStream_t);
 void skd_set_tf32_tma_type(int use_tfloat32_type);
 void skd_set_wgrad_linear(int on);     /* 1 (default): wgrad K-blocks are 32 consecutive pixels (im2col TMA); 0: 4x8 rectangles */
+void skd_set_conv_res_prefetch(int on); /* 1 (default): residual tiles prefetched with cp.async into a spare pipeline stage */
 void skd_set_conv_im2col(int on);      /* 1 (default): TMA im2col-mode M tiles for k>1 / strided convs; 0: rectangular tiled-mode tiles */
 
 /* ---- E. pooling / resampling / optimiser ---- */
 int skd_pool_out_size_ceil(int in, int k, int s, int p);
 int skd_maxpool3x3s2_fwd(int N, int H, int W, int C, const float* x, float* y, unsigned char* argmax, cudaStream_t);
 int skd_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy, const unsigned char* argmax, float* dx, cudaStream_t);
-int skd_psp_pool_fwd(int N, int H, int W, int C, const float* x, int x_pitch, int levels, const int* sizes, float* pooled, cudaStream_t);
+long long skd_psp_pool_workspace_floats(int N, int H, int C, int levels, const int* sizes);
+int skd_psp_pool_fwd(int N, int H, int W, int C, const float* x, int x_pitch, int levels, const int* sizes, float* pooled,
+                     float* workspace, cudaStream_t);
 int skd_psp_pool_bwd(int N, int H, int W, int C, const float* dpooled, int levels, const int* sizes, float* dx, cudaStream_t);
 int skd_psp_upsample_fwd(int N, int H, int W, int C, int s, const float* src, int nbins_total, int first_bin, float* out,
                          int out_pitch, int chan_off, cudaStream_t);
+long long skd_psp_upsample_bwd_workspace_floats(int N, int H, int C, int s);
 int skd_psp_upsample_bwd(int N, int H, int W, int C, int s, const float* dout, int dout_pitch, int chan_off, float* dsrc,
-                         int nbins_total, int first_bin, cudaStream_t);
+                         int nbins_total, int first_bin, float* workspace, cudaStream_t);
 int skd_slice_copy(long long rows, int C, const float* src, int src_pitch, int src_off, float* dst, int dst_pitch, int dst_off, cudaStream_t);
 /* G_solver.step (networks/kd_model.py:74,171): v = mu*v + (g*grad_scale + wd*p); p -= lr*v; lr read from device memory */
 int skd_sgd_step(long long n, float* param, const float* grad, float* momentum_buf, const float* lr, float momentum,

@@ -47,6 +47,8 @@ struct ConvArgs {
   int act; float slope; int round_out;
   int vec_ok;
   int tma_store;
+  int nstages;                     // pipeline stages in use (one fewer when the last stage buffer prefetches the residual)
+  int res_prefetch;                // residual tiles are cp.async-prefetched one chunk ahead into the spare stage buffer
   int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
 };
 
@@ -67,7 +69,9 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                       const __grid_constant__ CUtensorMap tmap_y, const ConvArgs a) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer in the shared address space (integer round trips make nvcc emit generic LD/ST instead of LDS/STS)
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* out_stage = smem + C::kStages * C::kStageBytes;                   // 2 x 16 KB, 1024-aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * C::kOutStageBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
@@ -128,7 +132,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             else
               ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
             ptx::tma_load_3d(sb, &tmap_w, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            if (++stage == a.nstages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -159,7 +163,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           if (k == k_iters - 1) ptx::mma_commit(&tmem_full[acc]);
         }
         __syncwarp();
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == a.nstages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -174,6 +178,27 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int dy = row / a.BW, dx = row - dy * a.BW;
     uint8_t* stg = out_stage + group * C::kOutStageBytes;
     int acc = 0; uint32_t acc_phase = 0;
+    const int gt = (ew & 3) * 32 + lane, ck = gt & 7;            // coalesced mapping: 8 threads per 128-byte pixel row
+    uint8_t* resbuf = smem + (C::kStages - 1) * C::kStageBytes + group * C::kOutStageBytes;   // spare stage buffer (res_prefetch)
+    auto prefetch_residual = [&](int t, int chunk) {
+      if (t < total_tiles) {
+        const int mt_ = t / a.n_tiles, nt_ = t - mt_ * a.n_tiles;
+        const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
+        const int ty_ = rem_ / a.tiles_x, tx_ = rem_ - ty_ * a.tiles_x;
+        const int cc = nt_ * BLOCK_N + chunk * 32 + ck * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 16 + (gt >> 3);
+          const int roy = ty_ * a.BH + rr / a.BW, rox = tx_ * a.BW + rr % a.BW;
+          const bool ok = roy < a.OH && rox < a.OW && cc + 3 < a.Cout;
+          const float* src = ok ? a.residual + (((size_t)img_ * a.OH + roy) * a.OW + rox) * a.ldr + cc : a.residual;
+          ptx::cp_async16(resbuf + rr * 128 + (ck << 4), src, ok ? 16 : 0);
+        }
+      }
+      ptx::cp_async_commit();
+    };
+    int pf_tile = -1, pf_chunk = -1;                               // what resbuf currently holds / is being filled with
+    if (a.res_prefetch) { prefetch_residual(blockIdx.x, group); pf_tile = blockIdx.x; pf_chunk = group; }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
       const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
@@ -201,11 +226,11 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int c0 = nt * BLOCK_N + ch * 32;
         if (c0 >= a.Cout) break;                                               // CTA-uniform
         // residual tile read COALESCED (8 threads cover the 128 B of one pixel row, a warp covers 4 rows; the per-row
-        // mapping of the TMEM load would touch 32 lines per instruction), issued before the TMEM load to overlap its latency
+        // mapping of the TMEM load would touch 32 lines per instruction).  Either prefetched one chunk ahead with cp.async
+        // into the spare pipeline-stage buffer (res_prefetch) or loaded into registers here, before the TMEM load.
         const bool coalesced_res = (a.residual != nullptr) && a.tma_store && a.vec_ok;      // CTA-uniform
         float4 q[8];
-        const int gt = (ew & 3) * 32 + lane, ck = gt & 7;
-        if (coalesced_res) {
+        if (coalesced_res && !a.res_prefetch) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 16 + (gt >> 3);
@@ -261,6 +286,12 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           if (coalesced_res) {
             // residual add + activation on the staged tile (residual registers were loaded coalesced above)
             ptx::named_bar_sync(1 + group, 128);
+            if (a.res_prefetch) {
+              if (pf_tile != tile || pf_chunk != ch) prefetch_residual(tile, ch);   // chain broken (ragged Cout): fetch now
+              ptx::cp_async_wait_all();                                         // this thread's own 8 x 16 B have landed
+#pragma unroll
+              for (int i = 0; i < 8; ++i) q[i] = *reinterpret_cast<const float4*>(resbuf + (i * 16 + (gt >> 3)) * 128 + (ck << 4));
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 16 + (gt >> 3);
@@ -281,6 +312,12 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           if (is_store_leader) {
             ptx::tma_store_4d(&tmap_y, stg, c0, tx * a.BW, ty * a.BH, img);
             ptx::bulk_commit();
+          }
+          if (a.res_prefetch) {                                                 // next chunk of this group: same tile or next tile
+            int ntile = tile, nch = ch + 2;
+            if (nch >= BLOCK_N / 32 || nt * BLOCK_N + nch * 32 >= a.Cout) { ntile = tile + gridDim.x; nch = group; }
+            prefetch_residual(ntile, nch);
+            pf_tile = ntile; pf_chunk = nch;
           }
         } else if (valid) {
 #pragma unroll
@@ -331,6 +368,7 @@ EncodeIm2colFn get_encode_im2col() {
   return fn;
 }
 int g_conv_im2col = 1;
+int g_res_prefetch = 1;
 
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
@@ -374,8 +412,12 @@ void pick_rect(int OH, int OW, int stride, int* BH, int* BW) {
 }
 
 template <int BLOCK_N>
-int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvArgs& a, cudaStream_t st) {
+int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvArgs& a_in, cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
+  ConvArgs a = a_in;
+  // residual epilogues on short-K convolutions: trade one pipeline stage for a cp.async residual prefetch buffer
+  a.res_prefetch = (a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && C::kStageBytes >= 2 * C::kOutStageBytes && C::kStages >= 4;
+  a.nstages = a.res_prefetch ? C::kStages - 1 : C::kStages;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_sm100_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -391,6 +433,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
 }  // namespace
 
 extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
+extern "C" void skd_set_conv_res_prefetch(int on) { g_res_prefetch = on ? 1 : 0; }
 
 static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                          const float* x, int ldx, const float* w, float* y, int ldy, long long y_row, long long y_img, int oh_req,
@@ -461,6 +504,7 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     if (!encode(&tw, 3, w, dims, strides, box, estr, who)) return 0;
   }
   CUtensorMap ty = tx;
+  a.nstages = 0; a.res_prefetch = 0;
   a.tma_store = (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) && (y_row % 4 == 0) && (y_img % 4 == 0);
   if (strided_out && (!a.tma_store || residual)) { set_error_msg(who, "strided output needs 16-byte aligned strides and no residual"); return 0; }
   if (a.tma_store) {

@@ -96,36 +96,53 @@ __device__ __forceinline__ void bin_of(const Pyramid& p, int bin, int& lvl, int&
 __device__ __forceinline__ int bin_lo(int i, int in, int s) { return (i * in) / s; }                  // floor
 __device__ __forceinline__ int bin_hi(int i, int in, int s) { return ((i + 1) * in + s - 1) / s; }    // ceil
 
-// pooled[n][bin][c]; block = 64 channel lanes x 16 pixel lanes (4 independent loads in flight per thread)
+// Separable pyramid pooling, one pass over the feature map for ALL levels:
+//   stage 1: rowbins[n][y][xb][c] = sum_{x in x-bin xb} x[n][y][x][c]      (xb runs over the 1+2+3+6 x-bins of all levels)
+//   stage 2: pooled[n][bin][c]    = sum_{y in y-bin} rowbins[n][y][xb(bin)][c] / area
 constexpr int kPoolLanes = 16;
-__global__ void __launch_bounds__(64 * kPoolLanes)
-psp_pool_fwd_kernel(const float* __restrict__ x, int pitch, int C, int H, int W, Pyramid p, float* __restrict__ pooled) {
-  __shared__ float sv[64 * kPoolLanes];
-  const int bin = blockIdx.x, n = blockIdx.y, cx = threadIdx.x & 63, lane = threadIdx.x >> 6, c = blockIdx.z * 64 + cx;
-  int lvl, by, bx; bin_of(p, bin, lvl, by, bx);
-  const int s = p.size[lvl];
-  const int y0 = bin_lo(by, H, s), y1 = bin_hi(by, H, s), x0 = bin_lo(bx, W, s), x1 = bin_hi(bx, W, s);
-  const int ww = x1 - x0, cnt = (y1 - y0) * ww;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+constexpr int kMaxXBins = 16;
+struct XBins { int n; int lo[kMaxXBins]; int hi[kMaxXBins]; };
+
+__global__ void __launch_bounds__(256)
+psp_rowbins_kernel(const float* __restrict__ x, int pitch, int C, int H, int W, XBins xb, float* __restrict__ rowbins) {
+  __shared__ float sv[3][kMaxXBins][64];
+  const int y = blockIdx.x, n = blockIdx.y, cx = threadIdx.x & 63, lane = threadIdx.x >> 6, c = blockIdx.z * 64 + cx;
+  float acc[kMaxXBins];
+#pragma unroll
+  for (int b = 0; b < kMaxXBins; ++b) acc[b] = 0.f;
   if (c < C) {
-    const float* base = x + (size_t)n * H * W * pitch + c;
-    int k = lane;
-    for (; k + 3 * kPoolLanes < cnt; k += 4 * kPoolLanes) {
-      const int k1 = k + kPoolLanes, k2 = k + 2 * kPoolLanes, k3 = k + 3 * kPoolLanes;
-      a0 += __ldg(base + ((size_t)(y0 + k / ww) * W + x0 + k % ww) * pitch);
-      a1 += __ldg(base + ((size_t)(y0 + k1 / ww) * W + x0 + k1 % ww) * pitch);
-      a2 += __ldg(base + ((size_t)(y0 + k2 / ww) * W + x0 + k2 % ww) * pitch);
-      a3 += __ldg(base + ((size_t)(y0 + k3 / ww) * W + x0 + k3 % ww) * pitch);
+    const float* base = x + ((size_t)n * H + y) * W * pitch + c;
+    for (int xx = lane; xx < W; xx += 4) {
+      const float v = __ldg(base + (size_t)xx * pitch);
+#pragma unroll
+      for (int b = 0; b < kMaxXBins; ++b) if (b < xb.n && xx >= xb.lo[b] && xx < xb.hi[b]) acc[b] += v;
     }
-    for (; k < cnt; k += kPoolLanes) a0 += __ldg(base + ((size_t)(y0 + k / ww) * W + x0 + k % ww) * pitch);
   }
-  sv[threadIdx.x] = (a0 + a1) + (a2 + a3);
+  if (lane > 0) {
+#pragma unroll
+    for (int b = 0; b < kMaxXBins; ++b) sv[lane - 1][b][cx] = acc[b];
+  }
   __syncthreads();
   if (lane == 0 && c < C) {
-    float a = 0.f;
-    for (int l = 0; l < kPoolLanes; ++l) a += sv[l * 64 + cx];
-    pooled[((size_t)n * gridDim.x + bin) * C + c] = a / (float)cnt;
+    float* out = rowbins + (((size_t)n * H + y) * xb.n) * C + c;
+#pragma unroll
+    for (int b = 0; b < kMaxXBins; ++b) if (b < xb.n) out[(size_t)b * C] = acc[b] + sv[0][b][cx] + sv[1][b][cx] + sv[2][b][cx];
   }
+}
+
+__global__ void __launch_bounds__(256)
+psp_colbins_kernel(const float* __restrict__ rowbins, int C, int H, int W, Pyramid p, int nxb, float* __restrict__ pooled) {
+  const int bin = blockIdx.x, n = blockIdx.y, c = blockIdx.z * 256 + threadIdx.x;
+  if (c >= C) return;
+  int lvl, by, bx; bin_of(p, bin, lvl, by, bx);
+  const int s = p.size[lvl];
+  int xoff = 0;
+  for (int l = 0; l < lvl; ++l) xoff += p.size[l];
+  const int y0 = bin_lo(by, H, s), y1 = bin_hi(by, H, s), x0 = bin_lo(bx, W, s), x1 = bin_hi(bx, W, s);
+  const float* src = rowbins + ((size_t)n * H * nxb + (xoff + bx)) * C + c;
+  float a = 0.f;
+  for (int y = y0; y < y1; ++y) a += __ldg(src + (size_t)y * nxb * C);
+  pooled[((size_t)n * gridDim.x + bin) * C + c] = a / (float)((y1 - y0) * (x1 - x0));
 }
 
 // dx[n][y][x][c] = sum over bins containing (y,x) of dpooled/area
@@ -139,10 +156,11 @@ psp_pool_bwd_kernel(const float* __restrict__ dpooled, int C4, int H, int W, int
     float4 g = make_float4(0, 0, 0, 0);
     for (int l = 0; l < p.levels; ++l) {
       const int s = p.size[l];
-      for (int by = 0; by < s; ++by) {
+      const int cy = (yy * s) / H, cxb = (xx * s) / W;           // the bin that certainly holds the pixel; neighbours may overlap
+      for (int by = max(cy - 1, 0); by <= min(cy + 1, s - 1); ++by) {
         const int y0 = bin_lo(by, H, s), y1 = bin_hi(by, H, s);
         if (yy < y0 || yy >= y1) continue;
-        for (int bx = 0; bx < s; ++bx) {
+        for (int bx = max(cxb - 1, 0); bx <= min(cxb + 1, s - 1); ++bx) {
           const int x0 = bin_lo(bx, W, s), x1 = bin_hi(bx, W, s);
           if (xx < x0 || xx >= x1) continue;
           const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
@@ -185,39 +203,52 @@ psp_up_fwd_kernel(const float* __restrict__ src, int C4, int s, int nb_total, in
   }
 }
 
-// dsrc[n][first_bin + iy*s+ix][c] = sum_{y,x} wy*wx * dout[n][y][x][coff + c]; block per (bin, n, 64 channels), 16 pixel
-// lanes over the bin's support only (rows/cols whose bilinear footprint touches source cell (iy, ix))
-__global__ void __launch_bounds__(64 * kPoolLanes)
-psp_up_bwd_kernel(const float* __restrict__ dout, int pitch, int coff, int C, int s, int nb_total, int first_bin,
-                  float* __restrict__ dsrc, int H, int W) {
-  __shared__ float sv[64 * kPoolLanes];
-  const int bin = blockIdx.x, n = blockIdx.y, cx = threadIdx.x & 63, lane = threadIdx.x >> 6, c = blockIdx.z * 64 + cx;
-  const int iy = bin / s, ix = bin - iy * s;
-  const float sy = H > 1 ? (float)(s - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(s - 1) / (float)(W - 1) : 0.f;
-  int ylo = 0, yhi = H - 1, xlo = 0, xhi = W - 1;
-  if (sy > 0.f) { ylo = max(0, (int)floorf((float)(iy - 1) / sy) - 1); yhi = min(H - 1, (int)ceilf((float)(iy + 1) / sy) + 1); }
-  if (sx > 0.f) { xlo = max(0, (int)floorf((float)(ix - 1) / sx) - 1); xhi = min(W - 1, (int)ceilf((float)(ix + 1) / sx) + 1); }
-  const int ww = xhi - xlo + 1, cnt = (yhi - ylo + 1) * ww;
-  float a = 0.f;
+// Bilinear-upsample backward, separable:  dsrc[n][iy][ix][c] = sum_y wy(y,iy) * ( sum_x wx(x,ix) * dout[n][y][x][coff+c] )
+//   stage 1 (per output row y): T[n][y][ix][c] for the s source columns;   stage 2: weighted sum over the rows.
+__global__ void __launch_bounds__(256)
+psp_up_bwd_rows_kernel(const float* __restrict__ dout, int pitch, int coff, int C, int s, float* __restrict__ T, int H, int W) {
+  __shared__ float sv[3][6][64];
+  const int y = blockIdx.x, n = blockIdx.y, cx = threadIdx.x & 63, lane = threadIdx.x >> 6, c = blockIdx.z * 64 + cx;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    const float* base = dout + (size_t)n * H * W * pitch + coff + c;
-    for (int k = lane; k < cnt; k += kPoolLanes) {
-      const int yy = ylo + k / ww, xx = xlo + k % ww;
-      const Lin by = lin(yy, s, H);
-      float wy = 0.f; if (by.i0 == iy) wy += by.l0; if (by.i1 == iy) wy += by.l1;
+    const float* base = dout + ((size_t)n * H + y) * W * pitch + coff + c;
+    for (int xx = lane; xx < W; xx += 4) {
+      const float v = __ldg(base + (size_t)xx * pitch);
       const Lin bx = lin(xx, s, W);
-      float wx = 0.f; if (bx.i0 == ix) wx += bx.l0; if (bx.i1 == ix) wx += bx.l1;
-      const float wgt = wy * wx;
-      if (wgt != 0.f) a += wgt * __ldg(base + ((size_t)yy * W + xx) * pitch);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        float wgt = 0.f;
+        if (bx.i0 == k) wgt += bx.l0;
+        if (bx.i1 == k) wgt += bx.l1;
+        acc[k] += wgt * v;
+      }
     }
   }
-  sv[threadIdx.x] = a;
+  if (lane > 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sv[lane - 1][k][cx] = acc[k];
+  }
   __syncthreads();
   if (lane == 0 && c < C) {
-    float t = 0.f;
-    for (int l = 0; l < kPoolLanes; ++l) t += sv[l * 64 + cx];
-    dsrc[((size_t)n * nb_total + first_bin + bin) * C + c] = t;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (k < s) T[(((size_t)n * H + y) * s + k) * C + c] = acc[k] + sv[0][k][cx] + sv[1][k][cx] + sv[2][k][cx];
   }
+}
+
+__global__ void __launch_bounds__(256)
+psp_up_bwd_cols_kernel(const float* __restrict__ T, int C, int s, int nb_total, int first_bin, float* __restrict__ dsrc, int H) {
+  const int bin = blockIdx.x, n = blockIdx.y, c = blockIdx.z * 256 + threadIdx.x;
+  if (c >= C) return;
+  const int iy = bin / s, ix = bin - iy * s;
+  float a = 0.f;
+  for (int y = 0; y < H; ++y) {
+    const Lin by = lin(y, s, H);
+    float wy = 0.f;
+    if (by.i0 == iy) wy += by.l0;
+    if (by.i1 == iy) wy += by.l1;
+    if (wy != 0.f) a += wy * __ldg(T + (((size_t)n * H + y) * s + ix) * C + c);
+  }
+  dsrc[((size_t)n * nb_total + first_bin + bin) * C + c] = a;
 }
 
 // strided channel-slice copy: dst[row][doff + c] = src[row][soff + c]
@@ -279,12 +310,26 @@ extern "C" int skd_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy,
   return finish("skd_maxpool3x3s2_bwd");
 }
 
+extern "C" long long skd_psp_pool_workspace_floats(int N, int H, int C, int levels, const int* sizes) {
+  int nxb = 0;
+  for (int i = 0; i < levels; ++i) nxb += sizes[i];
+  return (long long)N * H * nxb * C;
+}
+
 extern "C" int skd_psp_pool_fwd(int N, int H, int W, int C, const float* x, int x_pitch, int levels, const int* sizes,
-                                float* pooled, cudaStream_t st) {
+                                float* pooled, float* workspace, cudaStream_t st) {
   if (levels < 1 || levels > 4) { set_error_msg("skd_psp_pool_fwd", "1..4 pyramid levels"); return 0; }
   const Pyramid p = make_pyramid(levels, sizes);
-  psp_pool_fwd_kernel<<<dim3(p.first_bin[levels], N, (C + 63) / 64), 64 * kPoolLanes, 0, st>>>(x, x_pitch, C, H, W, p, pooled);
-  return finish("skd_psp_pool_fwd");
+  XBins xb; xb.n = 0;
+  for (int l = 0; l < levels; ++l)
+    for (int b = 0; b < sizes[l]; ++b) {
+      if (xb.n >= kMaxXBins) { set_error_msg("skd_psp_pool_fwd", "more than 16 x-bins over all levels"); return 0; }
+      xb.lo[xb.n] = (b * W) / sizes[l]; xb.hi[xb.n] = ((b + 1) * W + sizes[l] - 1) / sizes[l]; ++xb.n;
+    }
+  for (int b = xb.n; b < kMaxXBins; ++b) { xb.lo[b] = 0; xb.hi[b] = 0; }
+  psp_rowbins_kernel<<<dim3(H, N, (C + 63) / 64), 256, 0, st>>>(x, x_pitch, C, H, W, xb, workspace);
+  psp_colbins_kernel<<<dim3(p.first_bin[levels], N, (C + 255) / 256), 256, 0, st>>>(workspace, C, H, W, p, xb.n, pooled);
+  return finish("skd_psp_pool_fwd", 2);
 }
 
 extern "C" int skd_psp_pool_bwd(int N, int H, int W, int C, const float* dpooled, int levels, const int* sizes, float* dx,
@@ -303,11 +348,14 @@ extern "C" int skd_psp_upsample_fwd(int N, int H, int W, int C, int s, const flo
   return finish("skd_psp_upsample_fwd");
 }
 
+extern "C" long long skd_psp_upsample_bwd_workspace_floats(int N, int H, int C, int s) { return (long long)N * H * s * C; }
+
 extern "C" int skd_psp_upsample_bwd(int N, int H, int W, int C, int s, const float* dout, int dout_pitch, int chan_off,
-                                    float* dsrc, int nbins_total, int first_bin, cudaStream_t st) {
-  psp_up_bwd_kernel<<<dim3(s * s, N, (C + 63) / 64), 64 * kPoolLanes, 0, st>>>(dout, dout_pitch, chan_off, C, s, nbins_total, first_bin,
-                                                                  dsrc, H, W);
-  return finish("skd_psp_upsample_bwd");
+                                    float* dsrc, int nbins_total, int first_bin, float* workspace, cudaStream_t st) {
+  if (s < 1 || s > 6) { set_error_msg("skd_psp_upsample_bwd", "pyramid level size must be 1..6"); return 0; }
+  psp_up_bwd_rows_kernel<<<dim3(H, N, (C + 63) / 64), 256, 0, st>>>(dout, dout_pitch, chan_off, C, s, workspace, H, W);
+  psp_up_bwd_cols_kernel<<<dim3(s * s, N, (C + 255) / 256), 256, 0, st>>>(workspace, C, s, nbins_total, first_bin, dsrc, H);
+  return finish("skd_psp_upsample_bwd", 2);
 }
 
 extern "C" int skd_slice_copy(long long rows, int C, const float* src, int src_pitch, int src_off, float* dst, int dst_pitch,

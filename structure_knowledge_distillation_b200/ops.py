@@ -295,7 +295,9 @@ def psp_pool_fwd(x, sizes):
     pooled = torch.empty((n, nb, c), device=x.device, dtype=torch.float32)
     arr = _sizes_arr(sizes)
     import ctypes
-    lib().skd_psp_pool_fwd(n, h, w, c, _p(x), pitch, len(sizes), ctypes.cast(arr, ctypes.c_void_p), _p(pooled), _st())
+    ap = ctypes.cast(arr, ctypes.c_void_p)
+    ws = torch.empty(lib().skd_psp_pool_workspace_floats(n, h, c, len(sizes), ap), device=x.device, dtype=torch.float32)
+    lib().skd_psp_pool_fwd(n, h, w, c, _p(x), pitch, len(sizes), ap, _p(pooled), _p(ws), _st())
     return pooled
 
 
@@ -318,7 +320,8 @@ def psp_upsample_fwd(stage, s, out, chan_off):
 def psp_upsample_bwd(dout, s, c, chan_off):
     n, ctot, h, w, pitch = nhwc_meta(dout)
     dstage = torch.empty((n, s * s, c), device=dout.device, dtype=torch.float32)
-    lib().skd_psp_upsample_bwd(n, h, w, c, s, _p(dout), pitch, chan_off, _p(dstage), s * s, 0, _st())
+    ws = torch.empty(lib().skd_psp_upsample_bwd_workspace_floats(n, h, c, s), device=dout.device, dtype=torch.float32)
+    lib().skd_psp_upsample_bwd(n, h, w, c, s, _p(dout), pitch, chan_off, _p(dstage), s * s, 0, _p(ws), _st())
     return dstage
 
 

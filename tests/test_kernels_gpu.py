@@ -244,6 +244,23 @@ def test_conv_fwd_tcgen05(ops, case):
     lib().skd_set_conv_im2col(1)
 
 
+@pytest.mark.parametrize("N,Cin,H,W,Cout", [(8, 64, 9, 13, 288), (2, 128, 65, 129, 256), (3, 256, 10, 11, 1024), (2, 32, 7, 5, 160)])
+def test_conv_residual_epilogue_prefetch(ops, N, Cin, H, W, Cout):
+    """1x1 conv + folded BN + residual + ReLU (teacher Bottleneck conv3): cp.async residual prefetch chain, incl. ragged Cout."""
+    from structure_knowledge_distillation_b200._cabi import lib
+    g = torch.Generator(device="cuda").manual_seed(Cout)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 1, 1, device="cuda", generator=g) / Cin ** 0.5
+    sc = torch.rand(Cout, device="cuda", generator=g) + 0.5; sh = torch.randn(Cout, device="cuda", generator=g)
+    res = ops.to_nhwc(torch.randn(N, Cout, H, W, device="cuda", generator=g))
+    ref = torch.relu(_conv_ref64(x, w, 1, 0, 1) * sc.double()[None, :, None, None] + sh.double()[None, :, None, None] + res.double())
+    for pf in (0, 1):
+        lib().skd_set_conv_res_prefetch(pf)
+        out = ops.conv2d_fwd(ops.to_nhwc(x), ops.weight_ohwi(w), 1, 0, 1, scale=sc, shift=sh, residual=res, act="relu")
+        assert rel(out, ref) < 2e-3, (pf, rel(out, ref))
+    lib().skd_set_conv_res_prefetch(1)
+
+
 def test_conv_fwd_epilogue_and_pitch(ops):
     """folded-BN scale/shift + residual + ReLU, reading a channel slice and writing into a slice of a wider buffer."""
     g = torch.Generator(device="cuda").manual_seed(7)
