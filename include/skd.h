@@ -100,6 +100,20 @@ int skd_pairwise_gram(int N, int nodes, int CS, int CT, const float* pooled_S, c
 int skd_pairwise_bwd(int N, int nodes, int CS, const float* E, const float* pooled_S, const float* rnorm_S, const int* argmax,
                      const float* grad_out, float* dpooled, float* dF, long long sn, long long sc, long long sp, cudaStream_t);
 
+/* dF[argmax] = dpooled on a pre-zeroed feature gradient (second half of skd_pairwise_bwd) */
+int skd_pairwise_scatter(int N, int nodes, int CS, const float* dpooled, const int* argmax, float* dF, long long sn, long long sc,
+                         long long sp, cudaStream_t);
+/* tcgen05 path for large node counts (pool_scale -> 1/65: 8 385 nodes): E = [fT^|fS^] [fT^|-fS^]^T as one K-major TF32 GEMM per image with
+   the L2 reduction fused into the epilogue; E ([N][nodes][ldE], ldE % 4 == 0) may be NULL when no backward follows.  acc: 1 double. */
+long long skd_pairwise_affinity_sm100_workspace_floats(int N, int nodes, int CS, int CT);
+int skd_pairwise_affinity_sm100(int N, int nodes, int CS, int CT, const float* pooled_S, const float* pooled_T, const float* rnorm_S,
+                                const float* rnorm_T, float* E, int ldE, float* loss, float* workspace, double* acc, cudaStream_t);
+long long skd_pairwise_affinity_bwd_sm100_workspace_floats(int N, int nodes, int CS, int ldE);
+int skd_pairwise_affinity_bwd_sm100(int N, int nodes, int CS, const float* E, int ldE, const float* pooled_S, const float* rnorm_S,
+                                    const float* grad_out, float* dpooled, float* workspace, cudaStream_t);
+/* the tcgen05 conv kernel as a plain NT GEMM: D[M][Ncols] = A[M][K] B[Ncols][K]^T (D may be NULL), sumsq += sum D^2 (may be NULL) */
+int skd_gemm_nt_sm100(int M, int Ncols, int K, const float* A, int lda, const float* B, float* D, int ldd, double* sumsq, cudaStream_t);
+
 /* ---- D. convolutions (every nn.Conv2d of networks/pspnet_combine.py; cuDNN in the reference) ---- */
 /* tcgen05 implicit GEMM: y = act((conv(x,w))*scale + shift + residual); w is [Cout][KH][KW][Cin]; Cin % 4 == 0 */
 int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,

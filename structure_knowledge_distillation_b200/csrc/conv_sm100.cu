@@ -47,6 +47,8 @@ struct ConvArgs {
   int act; float slope; int round_out;
   int vec_ok;
   int tma_store;
+  double* sumsq;                   // optional: += sum of squares of every valid output element (fused L2 reduction)
+  int no_store;                    // 1: the output tensor is not written at all (reduction-only epilogue)
   int nstages;                     // pipeline stages in use (one fewer when the last stage buffer prefetches the residual)
   int res_prefetch;                // residual tiles are cp.async-prefetched one chunk ahead into the spare stage buffer
   int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
@@ -178,6 +180,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int dy = row / a.BW, dx = row - dy * a.BW;
     uint8_t* stg = out_stage + group * C::kOutStageBytes;
     int acc = 0; uint32_t acc_phase = 0;
+    double sq_acc = 0.0;
     const int gt = (ew & 3) * 32 + lane, ck = gt & 7;            // coalesced mapping: 8 threads per 128-byte pixel row
     uint8_t* resbuf = smem + (C::kStages - 1) * C::kStageBytes + group * C::kOutStageBytes;   // spare stage buffer (res_prefetch)
     auto prefetch_residual = [&](int t, int chunk) {
@@ -274,6 +277,13 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
           }
         }
+        if (a.sumsq && valid) {
+          float part = 0.f;                                                    // fp32 within a 32-element chunk, fp64 across chunks
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (c0 + j < a.Cout) part = fmaf(v[j], v[j], part);
+          sq_acc += (double)part;
+        }
+        if (a.no_store) continue;
         if (a.tma_store) {
           // stage the chunk in shared memory (128B-swizzled rows) and let the TMA engine write the BH x BW x 32 box:
           // fully coalesced, asynchronous, and pixels / channels outside the tensor are clipped by the hardware.
@@ -338,6 +348,10 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (is_store_leader) ptx::bulk_wait<0>();
+    if (a.sumsq) {
+      for (int o = 16; o > 0; o >>= 1) sq_acc += __shfl_xor_sync(0xffffffffu, sq_acc, o);
+      if (lane == 0) atomicAdd(a.sumsq, sq_acc);
+    }
   }
 
   ptx::tc_fence_before();
@@ -437,7 +451,7 @@ extern "C" void skd_set_conv_res_prefetch(int on) { g_res_prefetch = on ? 1 : 0;
 
 static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                          const float* x, int ldx, const float* w, float* y, int ldy, long long y_row, long long y_img, int oh_req,
-                         int ow_req, const float* scale, const float* shift, const float* residual, int ldr, int act, float slope,
+                         int ow_req, double* sumsq, int no_store, const float* scale, const float* shift, const float* residual, int ldr, int act, float slope,
                          int round_tf32, cudaStream_t st) {
   const char* who = "skd_conv2d_fwd_sm100";
   if (Cin % 4 || ldx % 4 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
@@ -504,8 +518,8 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     if (!encode(&tw, 3, w, dims, strides, box, estr, who)) return 0;
   }
   CUtensorMap ty = tx;
-  a.nstages = 0; a.res_prefetch = 0;
-  a.tma_store = (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) && (y_row % 4 == 0) && (y_img % 4 == 0);
+  a.nstages = 0; a.res_prefetch = 0; a.sumsq = sumsq; a.no_store = no_store;
+  a.tma_store = !no_store && (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) && (y_row % 4 == 0) && (y_img % 4 == 0);
   if (strided_out && (!a.tma_store || residual)) { set_error_msg(who, "strided output needs 16-byte aligned strides and no residual"); return 0; }
   if (a.tma_store) {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)a.N};
@@ -528,13 +542,21 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
                                     const float* shift, const float* residual, int ldr, int act, float slope,
                                     int round_tf32, cudaStream_t st) {
   const int OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
-  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, ldx, w, y, ldy, (long long)OW * ldy, (long long)OH * OW * ldy, 0, 0,
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, ldx, w, y, ldy, (long long)OW * ldy, (long long)OH * OW * ldy, 0, 0, nullptr, 0,
                        scale, shift, residual, ldr, act, slope, round_tf32, st);
 }
 
 extern "C" int skd_conv2d_fwd_sm100_strided(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                                             const float* x, int ldx, const float* w, float* y, long long y_pix, long long y_row,
                                             long long y_img, int out_h, int out_w, int round_tf32, cudaStream_t st) {
-  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, ldx, w, y, (int)y_pix, y_row, y_img, out_h, out_w, nullptr, nullptr, nullptr, 0,
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, ldx, w, y, (int)y_pix, y_row, y_img, out_h, out_w, nullptr, 0, nullptr, nullptr, nullptr, 0,
                        0, 0.f, round_tf32, st);
+}
+
+// GEMM view of the same kernel for the pair-wise affinity (utils/utils.py:173-183): D[M][Ncols] = A[M][K] * B[Ncols][K]^T with both
+// operands K-major; optional output, optional fused sum of squares.
+extern "C" int skd_gemm_nt_sm100(int M, int Ncols, int K, const float* A, int lda, const float* B, float* D, int ldd, double* sumsq,
+                                 cudaStream_t st) {
+  return conv_fwd_impl(1, 1, M, K, Ncols, 1, 1, 1, 0, 1, A, lda, B, D, ldd, (long long)M * ldd, (long long)M * ldd, 0, 0, sumsq,
+                       D == nullptr ? 1 : 0, nullptr, nullptr, nullptr, 0, 0, 0.f, 0, st);
 }

@@ -500,6 +500,12 @@ extern "C" int skd_pairwise_gram(int N, int nodes, int CS, int CT, const float* 
   return finish("skd_pairwise_gram", 2);
 }
 
+extern "C" int skd_pairwise_scatter(int N, int nodes, int CS, const float* dpooled, const int* argmax, float* dF, long long sn,
+                                    long long sc, long long sp, cudaStream_t st) {
+  pa_scatter_kernel<<<red_blocks((long long)N * nodes * CS), 256, 0, st>>>(dpooled, argmax, CS, nodes, N, dF, Strides{sn, sc, sp});
+  return finish("skd_pairwise_scatter");
+}
+
 extern "C" int skd_pairwise_bwd(int N, int nodes, int CS, const float* E, const float* pooled_S, const float* rnorm_S,
                                 const int* argmax, const float* grad_out, float* dpooled, float* dF, long long sn,
                                 long long sc, long long sp, cudaStream_t st) {

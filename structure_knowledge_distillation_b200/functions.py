@@ -28,11 +28,18 @@ class PixelWiseLoss(torch.autograd.Function):
 class PairWiseLoss(torch.autograd.Function):
     """CriterionPairWiseforWholeFeatAfterPool math (utils/criterion.py:236-245, utils/utils.py:170-183)."""
 
+    TCGEN05_MIN_NODES = 1024      # below: one SIMT tile kernel (the default pool_scale 0.5 has 9 nodes); above: tcgen05 GEMM
+
     @staticmethod
     def forward(ctx, feat_S, feat_T, ph, pw):
         pS, arg, rS = ops.pairwise_pool(feat_S, ph, pw, True)
         pT, _, rT = ops.pairwise_pool(feat_T, ph, pw, False)
-        loss, E = ops.pairwise_gram(pS, pT, rS, rT, True)
+        ctx.tensor_core = pS.shape[1] >= PairWiseLoss.TCGEN05_MIN_NODES and (pS.shape[2] + pT.shape[2]) % 4 == 0 and pS.shape[2] % 4 == 0
+        need_E = feat_S.requires_grad
+        if ctx.tensor_core:
+            loss, E = ops.pairwise_affinity_sm100(pS, pT, rS, rT, need_E)
+        else:
+            loss, E = ops.pairwise_gram(pS, pT, rS, rT, True)
         ctx.save_for_backward(E, pS, rS, arg, feat_S)
         return loss
 
@@ -40,6 +47,8 @@ class PairWiseLoss(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         E, pS, rS, arg, feat_S = ctx.saved_tensors
+        if ctx.tensor_core:
+            return ops.pairwise_affinity_bwd_sm100(E, pS, rS, arg, g.contiguous(), feat_S), None, None, None
         return ops.pairwise_bwd(E, pS, rS, arg, g.contiguous(), feat_S), None, None, None
 
 

@@ -415,5 +415,32 @@ def pairwise_bwd(E, pS, rS, arg, grad_out, feat_like):
     return dF
 
 
+def pairwise_affinity_sm100(pS, pT, rS, rT, want_E):
+    """tcgen05 large-node path: loss (0-dim) and E (N, nodes, ldE) or None."""
+    n, nodes, cs = pS.shape
+    ct = pT.shape[2]
+    L = lib()
+    ldE = pad4(nodes)
+    E = torch.empty((n, nodes, ldE), device=pS.device, dtype=torch.float32) if want_E else None
+    ws = torch.empty(L.skd_pairwise_affinity_sm100_workspace_floats(n, nodes, cs, ct), device=pS.device, dtype=torch.float32)
+    acc = torch.empty(1, device=pS.device, dtype=torch.float64)
+    loss = torch.empty((), device=pS.device, dtype=torch.float32)
+    L.skd_pairwise_affinity_sm100(n, nodes, cs, ct, _p(pS), _p(pT), _p(rS), _p(rT), _p(E), ldE, _p(loss), _p(ws), _p(acc), _st())
+    return loss, E
+
+
+def pairwise_affinity_bwd_sm100(E, pS, rS, arg, grad_out, feat_like):
+    n, nodes, cs = pS.shape
+    ldE = E.shape[2]
+    L = lib()
+    ws = torch.empty(L.skd_pairwise_affinity_bwd_sm100_workspace_floats(n, nodes, cs, ldE), device=pS.device, dtype=torch.float32)
+    dpooled = torch.empty_like(pS)
+    L.skd_pairwise_affinity_bwd_sm100(n, nodes, cs, _p(E), ldE, _p(pS), _p(rS), _p(grad_out), _p(dpooled), _p(ws), _st())
+    dF = torch.zeros(feat_like.shape, device=feat_like.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last) \
+        if feat_like.dim() == 4 and feat_like.stride(1) == 1 else torch.zeros_like(feat_like)
+    L.skd_pairwise_scatter(n, nodes, cs, _p(dpooled), _p(arg), _p(dF), *pixel_strides(dF), _st())
+    return dF
+
+
 def sgd_step(param, grad, buf, lr_dev, momentum, weight_decay, first, grad_scale=1.0):
     lib().skd_sgd_step(param.numel(), _p(param), _p(grad), _p(buf), _p(lr_dev), momentum, weight_decay, int(first), grad_scale, _st())

@@ -182,6 +182,33 @@ def test_losses_match_reference_goldens(ops, layout):
         assert rel(Sg[2].grad.cpu(), G["d_pa"]) < 2e-4, name
 
 
+@pytest.mark.parametrize("n,cs,ct,h,w", [(2, 32, 64, 33, 37), (1, 128, 512, 40, 43)])
+def test_pairwise_unpooled_tcgen05_vs_oracle(ops, n, cs, ct, h, w):
+    """pool window 1x1 (pool_scale -> 1/H): >= 1024 nodes -> tcgen05 GEMM with the L2 reduction in the epilogue; loss and
+    gradient against the CPU oracle (TF32 operands: 1e-3 on the loss, 1e-2 rel-L2 on the gradient)."""
+    from oracle import port
+    from structure_knowledge_distillation_b200 import functions as Fn
+    g = torch.Generator().manual_seed(h * w)
+    fS = (torch.randn(n, cs, h, w, generator=g) + 0.5).requires_grad_(True)
+    fT = torch.randn(n, ct, h, w, generator=g) + 0.5
+    ref = port.pairwise_loss(fS, fT, 1.0 / min(h, w) + 1e-9)             # int(h*s) == int(w*s) == 1: 1x1 pooling window
+    (gref,) = torch.autograd.grad(ref, fS)
+    assert h * w >= Fn.PairWiseLoss.TCGEN05_MIN_NODES
+    fSg = fS.detach().cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    loss = Fn.PairWiseLoss.apply(fSg, fT.cuda().contiguous(memory_format=torch.channels_last), 1, 1)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) / float(ref) < 1e-3, (float(loss), float(ref))
+    assert rel(fSg.grad.cpu(), gref) < 1e-2, rel(fSg.grad.cpu(), gref)
+    # the SIMT path on the same inputs agrees too
+    old = Fn.PairWiseLoss.TCGEN05_MIN_NODES
+    Fn.PairWiseLoss.TCGEN05_MIN_NODES = 10 ** 9
+    try:
+        l2 = Fn.PairWiseLoss.apply(fSg.detach().requires_grad_(True), fT.cuda().contiguous(memory_format=torch.channels_last), 1, 1)
+    finally:
+        Fn.PairWiseLoss.TCGEN05_MIN_NODES = old
+    assert abs(float(l2) - float(ref)) / float(ref) < 2e-5
+
+
 def test_pixelwise_full_size_properties(ops):
     """At BASELINE size (8,19,65,129): loss(S,S) == sum of entropies; gradient rows sum to zero; batch linearity."""
     g = torch.Generator(device="cuda").manual_seed(1)
