@@ -91,7 +91,7 @@ def run_reference(args, rank, world):
         return
     import torch
     from oracle import cases, port
-    cores = os.cpu_count()
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     cfg = port.StepConfig(pi=True, pa=True, ho=True, adv_type="wgan-gp")
     teacher, student, D = cases.build_models(seed=0, with_D=True)
@@ -115,10 +115,15 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def _cpu_threads():
+    # torch's CPU convolutions stop scaling (and on 100+ thread boxes get much slower) for a batch-1 step: cap at 32 threads
+    return min(os.cpu_count() or 1, 32)
+
+
 def cpu_baseline_leg():
     import torch
     from oracle import cases, port
-    cores = os.cpu_count()
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     cfg = port.StepConfig(pi=True, pa=True, ho=True, adv_type="wgan-gp")
     teacher, student, D = cases.build_models(seed=0, with_D=True)
@@ -229,12 +234,17 @@ def run_ours(args, rank, local_rank, world):
         return
     peaks = _peaks()
     tf32_peak = peaks["bf16_sus"] / 2.0                            # kind::tf32 issues at half the bf16 rate
+    wg_log = [r for r in conv_log if r[3][0] == "wgrad"]
+    all_log = conv_log
+    conv_log = [r for r in conv_log if r[3][0] != "wgrad"]         # the dominant kernel: conv_fwd_sm100_kernel (fwd + dgrad)
     conv_ms = sum(r[0].elapsed_time(r[1]) for r in conv_log)
     conv_flop = sum(r[2] for r in conv_log)
+    wg_ms = sum(r[0].elapsed_time(r[1]) for r in wg_log)
+    wg_flop = sum(r[2] for r in wg_log)
     if args.conv_table:
         import collections
         agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-        for r in conv_log:
+        for r in all_log:
             a = agg[r[3]]; a[0] += 1; a[1] += r[0].elapsed_time(r[1]); a[2] += r[2]
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
             print("CONV %-48s n=%3d  %7.3f ms/step  %6.0f TF" % (k, v[0] // args.steps, v[1] / args.steps, v[2] / v[1] / 1e9), file=sys.stderr)
@@ -259,6 +269,7 @@ def run_ours(args, rank, local_rank, world):
                      "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak if tf32_peak else None,
                      "peak_source": "%s bf16 sustained cuBLAS peak / 2 (TF32 operands)" % peaks["src"], "traffic": traffic,
                      "launches_timed": len(conv_log), "share_of_step": conv_ms / ms if ms else None,
+                     "wgrad_kernel": {"achieved": wg_flop / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else None, "share_of_step": wg_ms / ms if ms else None},
                      "measured_in": "eager pass of the same %d steps right after the timed region (%.2f ms/step)" % (args.steps, ms_eager / args.steps)},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -19,8 +19,8 @@ using namespace skd;
 namespace {
 
 constexpr int kBlockM = 128;               // Cout per tile
-constexpr int kKPix = 32;                  // pixels per stage
-constexpr int kChunkBytes = 32 * kKPix * 4;  // one 32-channel x 32-pixel box
+// pixels per pipeline stage: 64 for wide channel tiles, 128 for Cin <= 64 (fewer, larger TMA boxes: the producer is box-rate bound)
+__host__ __device__ constexpr int kpix_for(int block_n) { return block_n >= 128 ? 64 : 128; }
 constexpr int kThreads = 192;
 
 struct WgArgs {
@@ -33,10 +33,12 @@ struct WgArgs {
 
 template <int BLOCK_N>
 struct WCfg {
+  static constexpr int kKPix = kpix_for(BLOCK_N);
+  static constexpr int kChunkBytes = 32 * kKPix * 4;                 // one 32-channel x kKPix-pixel box
   static constexpr int kABytes = 4 * kChunkBytes;                    // 128 co
   static constexpr int kBBytes = (BLOCK_N / 32) * kChunkBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kStages = (BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 2);
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
@@ -73,41 +75,42 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
   const int kb_per_img = a.kb_x * a.kb_y;
 
   if (warp == 0) {
+    // ===================== TMA producer =====================
+    // TMA sustains roughly one box per ~100 cycles per SM whatever its size, so boxes are made as large as the MN-major
+    // swizzle allows (32 channels x 64 pixels = 8 KB) and all-out-of-range channel chunks (Cout or Cin < tile) are not issued.
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int tile = u / a.splits, split = u - tile * a.splits;
+        const int split = u / tiles, tile = u - split * tiles;
         const int mt = tile / (a.taps * a.n_tiles), r = tile - mt * (a.taps * a.n_tiles);
         const int tap = r / a.n_tiles, nt = r - tap * a.n_tiles;
         const int kh = tap / a.KW, kw = tap - kh * a.KW;
         const int kb0 = split * a.kb_per_split;
         const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
+        const int a_chunks = min(4, (a.Cout - mt * kBlockM + 31) / 32);
+        const int b_chunks = min(BLOCK_N / 32, (a.Cin - nt * BLOCK_N + 31) / 32);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
-          ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)((a_chunks + b_chunks) * C::kChunkBytes));
           if (a.linear) {
-            const int p0 = kb * kKPix;
+            const int p0 = kb * C::kKPix;
             const int img = p0 / (a.OH * a.OW), r2 = p0 - img * (a.OH * a.OW);
             const int oy = r2 / a.OW, ox = r2 - oy * a.OW;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              ptx::tma_load_4d(sa + c * kChunkBytes, &tmap_dy, &full_bar[stage], mt * kBlockM + c * 32, p0, 0, 0);
-#pragma unroll
-            for (int c = 0; c < BLOCK_N / 32; ++c)
-              ptx::tma_load_im2col_4d(sb + c * kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32, ox * a.stride - a.pad,
+            for (int c = 0; c < a_chunks; ++c)
+              ptx::tma_load_4d(sa + c * C::kChunkBytes, &tmap_dy, &full_bar[stage], mt * kBlockM + c * 32, p0, 0, 0);
+            for (int c = 0; c < b_chunks; ++c)
+              ptx::tma_load_im2col_4d(sb + c * C::kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32, ox * a.stride - a.pad,
                                       oy * a.stride - a.pad, img, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
           } else {
             const int img = kb / kb_per_img, q = kb - img * kb_per_img;
             const int by = q / a.kb_x, bx = q - by * a.kb_x;
             const int oy0 = by * a.BHk, ox0 = bx * a.BWk;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              ptx::tma_load_4d(sa + c * kChunkBytes, &tmap_dy, &full_bar[stage], mt * kBlockM + c * 32, ox0, oy0, img);
-#pragma unroll
-            for (int c = 0; c < BLOCK_N / 32; ++c)
-              ptx::tma_load_4d(sb + c * kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32,
+            for (int c = 0; c < a_chunks; ++c)
+              ptx::tma_load_4d(sa + c * C::kChunkBytes, &tmap_dy, &full_bar[stage], mt * kBlockM + c * 32, ox0, oy0, img);
+            for (int c = 0; c < b_chunks; ++c)
+              ptx::tma_load_4d(sb + c * C::kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32,
                                ox0 * a.stride - a.pad + kw * a.dil, oy0 * a.stride - a.pad + kh * a.dil, img);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -118,7 +121,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
     constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, BLOCK_N, 1, 1);     // both operands MN-major
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int tile = u / a.splits, split = u - tile * a.splits;
+      const int split = u / tiles, tile = u - split * tiles;
       const int kb0 = split * a.kb_per_split;
       const int nkb = min(a.kb_total, kb0 + a.kb_per_split) - kb0;
       if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -132,11 +135,11 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
           const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
 #pragma unroll
-          for (int kk = 0; kk < kKPix / 8; ++kk) {
+          for (int kk = 0; kk < C::kKPix / 8; ++kk) {
             // MN-major tf32 must use the 128B swizzle with 32B atoms (UMMA layout type 1 <-> TMA SWIZZLE_128B_ATOM_32B):
             // LBO = distance between 32-channel chunks, SBO = distance between 4-pixel groups
-            const uint64_t da = ptx::make_smem_desc(sa + kk * 1024, kChunkBytes, 512, 1);
-            const uint64_t db = ptx::make_smem_desc(sb + kk * 1024, kChunkBytes, 512, 1);
+            const uint64_t da = ptx::make_smem_desc(sa + kk * 1024, C::kChunkBytes, 512, 1);   // 8 pixels = 1 KB per MMA K step
+            const uint64_t db = ptx::make_smem_desc(sb + kk * 1024, C::kChunkBytes, 512, 1);
             ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
           }
           ptx::mma_commit(&empty_bar[stage]);
@@ -153,7 +156,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
     const size_t kdim = (size_t)a.taps * a.Cin;
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int tile = u / a.splits, split = u - tile * a.splits;
+      const int split = u / tiles, tile = u - split * tiles;
       const int mt = tile / (a.taps * a.n_tiles), r = tile - mt * (a.taps * a.n_tiles);
       const int tap = r / a.n_tiles, nt = r - tap * a.n_tiles;
       const int co = mt * kBlockM + row;
@@ -224,18 +227,27 @@ int g_wgrad_linear = 1;
 Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil) {
   Plan p;
   p.OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1; p.OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
-  const int cand[4][2] = {{4, 8}, {2, 16}, {8, 4}, {1, 32}};
+  const int cand[4][2] = {{8, 8}, {4, 16}, {16, 4}, {2, 32}};        // 64-pixel K blocks in the rectangular fallback mode
   long long best = -1;
   for (auto& c : cand) {
     const long long t = (long long)((p.OH + c[0] - 1) / c[0]) * ((p.OW + c[1] - 1) / c[1]);
     if (best < 0 || t < best) { best = t; p.BHk = c[0]; p.BWk = c[1]; }
   }
+  p.bn = Cin > 128 ? 256 : (Cin > 64 ? 128 : (Cin > 32 ? 64 : 32));
+  const int kpix = kpix_for(p.bn);
+  if (kpix == 128) {                                              // 128-pixel rectangles in the fallback mode
+    const int cand2[4][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}};
+    best = -1;
+    for (auto& c : cand2) {
+      const long long t = (long long)((p.OH + c[0] - 1) / c[0]) * ((p.OW + c[1] - 1) / c[1]);
+      if (best < 0 || t < best) { best = t; p.BHk = c[0]; p.BWk = c[1]; }
+    }
+  }
   p.kb_x = (p.OW + p.BWk - 1) / p.BWk; p.kb_y = (p.OH + p.BHk - 1) / p.BHk;
   p.kb_total = N * p.kb_x * p.kb_y;
   const int up_h = pad - (KH - 1) * dil, up_w = pad - (KW - 1) * dil;
   p.linear = g_wgrad_linear && pad <= 128 && up_h >= -128 && up_w >= -128 && stride <= 8 && (long long)N * p.OH * p.OW < (1LL << 31);
-  if (p.linear) p.kb_total = (int)(((long long)N * p.OH * p.OW + kKPix - 1) / kKPix);
-  p.bn = Cin > 128 ? 256 : (Cin > 64 ? 128 : (Cin > 32 ? 64 : 32));
+  if (p.linear) p.kb_total = (int)(((long long)N * p.OH * p.OW + kpix - 1) / kpix);
   p.m_tiles = (Cout + kBlockM - 1) / kBlockM; p.n_tiles = (Cin + p.bn - 1) / p.bn; p.taps = KH * KW;
   const int tiles = p.m_tiles * p.n_tiles * p.taps;
   int splits = (2 * kNumSMs + tiles - 1) / tiles;
@@ -301,7 +313,7 @@ extern "C" int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, in
     {
       cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)P, 1, 1};
       cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)P * ldy * 4, (cuuint64_t)P * ldy * 4};
-      cuuint32_t box[4] = {32, (cuuint32_t)kKPix, 1, 1};
+      cuuint32_t box[4] = {32, (cuuint32_t)kpix_for(p.bn), 1, 1};
       cuuint32_t es[4] = {1, 1, 1, 1};
       CUresult r = enc(&tdy, dt, 4, const_cast<float*>(dy), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -313,7 +325,7 @@ extern "C" int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, in
       int lower[2] = {-pad, -pad};
       int upper[2] = {pad - (KW - 1) * dil, pad - (KH - 1) * dil};
       cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-      CUresult r = enc_i2c(&tx, dt, 4, const_cast<float*>(x), dims, strides, lower, upper, 32, (cuuint32_t)kKPix, es,
+      CUresult r = enc_i2c(&tx, dt, 4, const_cast<float*>(x), dims, strides, lower, upper, 32, (cuuint32_t)kpix_for(p.bn), es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeIm2col(x) failed"); return 0; }

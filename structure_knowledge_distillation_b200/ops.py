@@ -251,7 +251,14 @@ def conv2d_wgrad(x, dy, kshape, stride, pad, dil, force_direct=False):
     else:
         nws = L.skd_conv2d_wgrad_sm100_workspace_floats(n, h, w, cin, cout, kh, kw, stride, pad, dil)
         ws = torch.empty(max(nws, 4), device=x.device, dtype=torch.float32)
+        log = CONV_EVENT_LOG
+        if log is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         L.skd_conv2d_wgrad_sm100(n, h, w, cin, cout, kh, kw, stride, pad, dil, _p(x), ldx, _p(dy), ldy, _p(dw), _p(ws), _st())
+        if log is not None:
+            ev1.record()
+            log.append((ev0, ev1, 2.0 * n * doh * dow * cout * cin * kh * kw, ("wgrad", n, cin, h, w, cout, kh, stride, dil)))
     return dw
 
 
