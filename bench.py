@@ -236,7 +236,7 @@ def run_ours(args, rank, local_rank, world):
     tf32_peak = peaks["bf16_sus"] / 2.0                            # kind::tf32 issues at half the bf16 rate
     wg_log = [r for r in conv_log if r[3][0] == "wgrad"]
     all_log = conv_log
-    conv_log = [r for r in conv_log if r[3][0] != "wgrad"]         # the dominant kernel: conv_fwd_sm100_kernel (fwd + dgrad)
+    conv_log = [r for r in conv_log if r[3][0] in ("fwd", "dgrad", "fwd3x")]         # the dominant kernel: conv_fwd_sm100_kernel (fwd + dgrad)
     conv_ms = sum(r[0].elapsed_time(r[1]) for r in conv_log)
     conv_flop = sum(r[2] for r in conv_log)
     wg_ms = sum(r[0].elapsed_time(r[1]) for r in wg_log)
@@ -247,7 +247,7 @@ def run_ours(args, rank, local_rank, world):
         for r in all_log:
             a = agg[r[3]]; a[0] += 1; a[1] += r[0].elapsed_time(r[1]); a[2] += r[2]
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
-            print("CONV %-48s n=%3d  %7.3f ms/step  %6.0f TF" % (k, v[0] // args.steps, v[1] / args.steps, v[2] / v[1] / 1e9), file=sys.stderr)
+            print("CONV %-48s n=%3d  %7.3f ms/step  %6.0f TF" % (k, v[0] // args.steps, v[1] / args.steps, v[2] / max(v[1], 1e-9) / 1e9), file=sys.stderr)
     achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_fwd_traffic.json")

@@ -119,6 +119,12 @@ int skd_gemm_nt_sm100(int M, int Ncols, int K, const float* A, int lda, const fl
 int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
                          int ldx, const float* w, float* y, int ldy, const float* scale, const float* shift,
                          const float* residual, int ldr, int act, float slope, int round_tf32, cudaStream_t);
+/* split-precision forward (x = x_hi + x_lo, w = w_hi + w_lo, all four TF32-exact): three accumulation passes in one launch, fp32-grade
+   result; skd_split_tf32 produces the parts (hi = rna_tf32(v), lo = rna_tf32(v - hi)) */
+int skd_conv2d_fwd_sm100_3xtf32(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x_hi,
+                                const float* x_lo, int ldx, const float* w_hi, const float* w_lo, float* y, int ldy, const float* scale,
+                                const float* shift, int act, float slope, cudaStream_t);
+int skd_split_tf32(long long n, const float* src, float* hi, float* lo, cudaStream_t);
 /* same kernel, output written through explicit element strides y[n*y_img + oy*y_row + ox*y_pix + c] (every-other-pixel sub-grids:
    the data gradient of a stride-2 convolution is 4 stride-1 convolutions of dy, one per input-pixel parity class) */
 int skd_conv2d_fwd_sm100_strided(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
@@ -137,6 +143,9 @@ int skd_conv2d_dgrad_direct(int N, int H, int W, int Cin, int Cout, int KH, int 
 int skd_conv2d_wgrad_direct(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
                             int ldx, const float* dy, int ldy, float* dw, cudaStream_t);
 int skd_colsum(long long P, int C, const float* dy, int ldy, float* db, cudaStream_t);
+/* explicit im2col for tiny-Cin convolutions (3-channel stem): col[N*OH*OW][Kp], k = (kh*KW+kw)*Cin+ci, zero padded to Kp */
+int skd_im2col_small(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int dil, const float* x, int ldx, float* col,
+                     int Kp, cudaStream_t);
 /* wt[Cin][KH][KW][Cout] = w[Cout][KH-1-kh][KW-1-kw][Cin] (dgrad of a stride-1 conv == forward conv with wt, pad' = d*(K-1)-pad) */
 int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w, float* wt, int round_tf32, cudaStream_t);
 int skd_round_tf32(long long n, const float* src, float* dst, cudaStream_t);

@@ -105,6 +105,32 @@ colsum_kernel(const float* __restrict__ dy, int ldy, long long P, int C, float* 
   }
 }
 
+// Explicit im2col for tiny-Cin convolutions (the 3-channel stem): col[p][(kh*KW+kw)*Cin + ci], zero padded to Kp columns.
+// With K = 27 a tensor-core implicit GEMM would spend 9 mostly-empty K steps per tile; one dense 32-wide K step on this
+// matrix (134 MB at batch 8) is 5x cheaper, and the weight gradient becomes a single-tap GEMM over the same matrix.
+__global__ void __launch_bounds__(256)
+im2col_small_kernel(Geo g, const float* __restrict__ x, int ldx, float* __restrict__ col, int Kp) {
+  const long long total = (long long)g.N * g.OH * g.OW * (Kp / 4);
+  const int K = g.KH * g.KW * g.Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k4 = (int)(i % (Kp / 4)); const long long p = i / (Kp / 4);
+    const int ox = (int)(p % g.OW); const long long r = p / g.OW; const int oy = (int)(r % g.OH), n = (int)(r / g.OH);
+    float v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k = k4 * 4 + t;
+      float val = 0.f;
+      if (k < K) {
+        const int ci = k % g.Cin, tap = k / g.Cin, kh = tap / g.KW, kw = tap - kh * g.KW;
+        const int iy = oy * g.stride - g.pad + kh * g.dil, ix = ox * g.stride - g.pad + kw * g.dil;
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) val = __ldg(x + (((size_t)n * g.H + iy) * g.W + ix) * ldx + ci);
+      }
+      v[t] = val;
+    }
+    reinterpret_cast<float4*>(col)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 int ew_blocks(long long total) {
   long long b = (total + 255) / 256;
   if (b > kNumSMs * 32) b = kNumSMs * 32;
@@ -158,4 +184,12 @@ extern "C" int skd_colsum(long long P, int C, const float* dy, int ldy, float* d
   if (split < 1) split = 1;
   colsum_kernel<<<dim3(bx, (unsigned)split), 256, 0, st>>>(dy, ldy, P, C, db);
   return finish("skd_colsum");
+}
+
+extern "C" int skd_im2col_small(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int dil, const float* x, int ldx,
+                                float* col, int Kp, cudaStream_t st) {
+  if (Kp % 4 || Kp < KH * KW * Cin) { set_error_msg("skd_im2col_small", "Kp must be a multiple of 4 and >= KH*KW*Cin"); return 0; }
+  const Geo g = make_geo(N, H, W, Cin, 1, KH, KW, stride, pad, dil);
+  im2col_small_kernel<<<ew_blocks((long long)N * g.OH * g.OW * (Kp / 4)), 256, 0, st>>>(g, x, ldx, col, Kp);
+  return finish("skd_im2col_small");
 }

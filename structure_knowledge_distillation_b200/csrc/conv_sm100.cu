@@ -49,6 +49,7 @@ struct ConvArgs {
   int tma_store;
   double* sumsq;                   // optional: += sum of squares of every valid output element (fused L2 reduction)
   int no_store;                    // 1: the output tensor is not written at all (reduction-only epilogue)
+  int passes;                      // 1: TF32;  3: split-precision 3xTF32 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32-grade result)
   int nstages;                     // pipeline stages in use (one fewer when the last stage buffer prefetches the residual)
   int res_prefetch;                // residual tiles are cp.async-prefetched one chunk ahead into the spare stage buffer
   int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
@@ -68,7 +69,8 @@ struct Cfg {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const __grid_constant__ CUtensorMap tmap_y, const ConvArgs a) {
+                      const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_x2,
+                      const __grid_constant__ CUtensorMap tmap_w2, const ConvArgs a) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the pointer in the shared address space (integer round trips make nvcc emit generic LD/ST instead of LDS/STS)
@@ -101,7 +103,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 
   const int total_tiles = a.m_tiles * a.n_tiles;
   const int taps = a.KH * a.KW;
-  const int k_iters = taps * a.k_chunks;
+  const int k_iters = a.passes * taps * a.k_chunks;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   if (warp == 0) {
@@ -122,6 +124,9 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           ip0 = (r2 / a.rOW) * a.stride - a.pad;
           iq0 = (r2 % a.rOW) * a.stride - a.pad;
         }
+        for (int pass = 0; pass < a.passes; ++pass) {
+        const CUtensorMap* mx = (pass == 1) ? &tmap_x2 : &tmap_x;      // pass 1 reads the low part of x, pass 2 the low part of w
+        const CUtensorMap* mw = (pass == 2) ? &tmap_w2 : &tmap_w;
         for (int tap = 0; tap < taps; ++tap) {
           const int kh = tap / a.KW, kw = tap - kh * a.KW;
           for (int kc = 0; kc < a.k_chunks; ++kc) {
@@ -130,12 +135,13 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             uint8_t* sb = sa + kABytes;
             ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
             if (a.im2col)
-              ptx::tma_load_im2col_4d(sa, &tmap_x, &full_bar[stage], kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
+              ptx::tma_load_im2col_4d(sa, mx, &full_bar[stage], kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
             else
-              ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
-            ptx::tma_load_3d(sb, &tmap_w, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
+              ptx::tma_load_4d(sa, mx, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
+            ptx::tma_load_3d(sb, mw, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
             if (++stage == a.nstages) { stage = 0; phase ^= 1; }
           }
+        }
         }
       }
     }
@@ -426,7 +432,8 @@ void pick_rect(int OH, int OW, int stride, int* BH, int* BW) {
 }
 
 template <int BLOCK_N>
-int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvArgs& a_in, cudaStream_t st) {
+int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx2, const CUtensorMap& tw2,
+           const ConvArgs& a_in, cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
   ConvArgs a = a_in;
   // residual epilogues on short-K convolutions: trade one pipeline stage for a cp.async residual prefetch buffer
@@ -440,7 +447,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   }
   int grid = a.m_tiles * a.n_tiles;
   if (grid > kNumSMs) grid = kNumSMs;
-  conv_fwd_sm100_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, ty, a);
+  conv_fwd_sm100_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tx2, tw2, a);
   return finish("skd_conv2d_fwd_sm100");
 }
 
@@ -450,7 +457,7 @@ extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
 extern "C" void skd_set_conv_res_prefetch(int on) { g_res_prefetch = on ? 1 : 0; }
 
 static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
-                         const float* x, int ldx, const float* w, float* y, int ldy, long long y_row, long long y_img, int oh_req,
+                         const float* x, const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, long long y_row, long long y_img, int oh_req,
                          int ow_req, double* sumsq, int no_store, const float* scale, const float* shift, const float* residual, int ldr, int act, float slope,
                          int round_tf32, cudaStream_t st) {
   const char* who = "skd_conv2d_fwd_sm100";
@@ -491,31 +498,40 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   const int bn = Cout > 128 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
   a.n_tiles = (Cout + bn - 1) / bn;
 
-  CUtensorMap tx, tw;
-  if (a.im2col) {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
-    int lower[2] = {-pad, -pad};                             // (W, H): filter origin of the first output pixel
-    int upper[2] = {up_w, up_h};                             // last filter origin = dim-1 + upper
-    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = get_encode_im2col()(&tx, g_tf32_tma_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
-                                     const_cast<float*>(x), dims, strides, lower, upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeIm2col failed"); return 0; }
-  } else {
+  CUtensorMap tx, tw, tx2, tw2;
+  auto encode_x = [&](CUtensorMap* m, const float* ptr) -> bool {
+    if (a.im2col) {
+      cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+      int lower[2] = {-pad, -pad};                             // (W, H): filter origin of the first output pixel
+      int upper[2] = {up_w, up_h};                             // last filter origin = dim-1 + upper
+      cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+      CUresult r = get_encode_im2col()(m, g_tf32_tma_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                       const_cast<float*>(ptr), dims, strides, lower, upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error_msg(who, "cuTensorMapEncodeIm2col failed"); return false; }
+      return true;
+    }
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)vW, (cuuint64_t)vH, (cuuint64_t)vN};
     cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)vW * ldx * 4, (cuuint64_t)vH * vW * ldx * 4};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(a.BW * stride), (cuuint32_t)(a.BH * stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    if (!encode(&tx, 4, x, dims, strides, box, estr, who)) return 0;
-  }
-  {
+    return encode(m, 4, ptr, dims, strides, box, estr, who);
+  };
+  auto encode_w = [&](CUtensorMap* m, const float* ptr) -> bool {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)(KH * KW), (cuuint64_t)Cout};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)KH * KW * Cin * 4};
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)bn};
     cuuint32_t estr[3] = {1, 1, 1};
-    if (!encode(&tw, 3, w, dims, strides, box, estr, who)) return 0;
+    return encode(m, 3, ptr, dims, strides, box, estr, who);
+  };
+  if (!encode_x(&tx, x) || !encode_w(&tw, w)) return 0;
+  tx2 = tx; tw2 = tw; a.passes = 1;
+  if (x_lo && w_lo) {                                          // split-precision operands: three accumulation passes
+    if ((reinterpret_cast<uintptr_t>(x_lo) | reinterpret_cast<uintptr_t>(w_lo)) & 15) { set_error_msg(who, "x_lo / w_lo not 16-byte aligned"); return 0; }
+    if (!encode_x(&tx2, x_lo) || !encode_w(&tw2, w_lo)) return 0;
+    a.passes = 3;
   }
   CUtensorMap ty = tx;
   a.nstages = 0; a.res_prefetch = 0; a.sumsq = sumsq; a.no_store = no_store;
@@ -530,10 +546,10 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     if (!encode(&ty, 4, y, dims, strides, box, estr, who, true)) return 0;
   }
   switch (bn) {
-    case 256: return launch<256>(tx, tw, ty, a, st);
-    case 128: return launch<128>(tx, tw, ty, a, st);
-    case 64: return launch<64>(tx, tw, ty, a, st);
-    default: return launch<32>(tx, tw, ty, a, st);
+    case 256: return launch<256>(tx, tw, ty, tx2, tw2, a, st);
+    case 128: return launch<128>(tx, tw, ty, tx2, tw2, a, st);
+    case 64: return launch<64>(tx, tw, ty, tx2, tw2, a, st);
+    default: return launch<32>(tx, tw, ty, tx2, tw2, a, st);
   }
 }
 
@@ -542,14 +558,14 @@ extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int 
                                     const float* shift, const float* residual, int ldr, int act, float slope,
                                     int round_tf32, cudaStream_t st) {
   const int OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
-  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, ldx, w, y, ldy, (long long)OW * ldy, (long long)OH * OW * ldy, 0, 0, nullptr, 0,
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, nullptr, ldx, w, nullptr, y, ldy, (long long)OW * ldy, (long long)OH * OW * ldy, 0, 0, nullptr, 0,
                        scale, shift, residual, ldr, act, slope, round_tf32, st);
 }
 
 extern "C" int skd_conv2d_fwd_sm100_strided(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                                             const float* x, int ldx, const float* w, float* y, long long y_pix, long long y_row,
                                             long long y_img, int out_h, int out_w, int round_tf32, cudaStream_t st) {
-  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, ldx, w, y, (int)y_pix, y_row, y_img, out_h, out_w, nullptr, 0, nullptr, nullptr, nullptr, 0,
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, nullptr, ldx, w, nullptr, y, (int)y_pix, y_row, y_img, out_h, out_w, nullptr, 0, nullptr, nullptr, nullptr, 0,
                        0, 0.f, round_tf32, st);
 }
 
@@ -557,6 +573,18 @@ extern "C" int skd_conv2d_fwd_sm100_strided(int N, int H, int W, int Cin, int Co
 // operands K-major; optional output, optional fused sum of squares.
 extern "C" int skd_gemm_nt_sm100(int M, int Ncols, int K, const float* A, int lda, const float* B, float* D, int ldd, double* sumsq,
                                  cudaStream_t st) {
-  return conv_fwd_impl(1, 1, M, K, Ncols, 1, 1, 1, 0, 1, A, lda, B, D, ldd, (long long)M * ldd, (long long)M * ldd, 0, 0, sumsq,
+  return conv_fwd_impl(1, 1, M, K, Ncols, 1, 1, 1, 0, 1, A, nullptr, lda, B, nullptr, D, ldd, (long long)M * ldd, (long long)M * ldd, 0, 0, sumsq,
                        D == nullptr ? 1 : 0, nullptr, nullptr, nullptr, 0, 0, 0.f, 0, st);
+}
+
+// Split-precision ("3xTF32") forward: x = x_hi + x_lo, w = w_hi + w_lo (each part exactly representable in TF32); the kernel
+// accumulates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in the same TMEM accumulator -> fp32-grade result at 3x the tensor work.
+// Used for the student's stem and layer1, where train-mode BN amplifies operand rounding the most (DESIGN.md "TF32 and parity").
+extern "C" int skd_conv2d_fwd_sm100_3xtf32(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                           const float* x_hi, const float* x_lo, int ldx, const float* w_hi, const float* w_lo,
+                                           float* y, int ldy, const float* scale, const float* shift, int act, float slope,
+                                           cudaStream_t st) {
+  const int OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x_hi, x_lo, ldx, w_hi, w_lo, y, ldy, (long long)OW * ldy,
+                       (long long)OH * OW * ldy, 0, 0, nullptr, 0, scale, shift, nullptr, 0, act, slope, 0, st);
 }

@@ -31,6 +31,15 @@ __global__ void __launch_bounds__(256) round_kernel(long long n, const float* __
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     d[i] = ptx::round_tf32(s[i]);
 }
+__global__ void __launch_bounds__(256) split_kernel(long long n4, const float4* __restrict__ s, float4* __restrict__ hi, float4* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = s[i]; float4 h, l;
+    h.x = ptx::round_tf32(v.x); h.y = ptx::round_tf32(v.y); h.z = ptx::round_tf32(v.z); h.w = ptx::round_tf32(v.w);
+    l.x = ptx::round_tf32(v.x - h.x); l.y = ptx::round_tf32(v.y - h.y); l.z = ptx::round_tf32(v.z - h.z); l.w = ptx::round_tf32(v.w - h.w);
+    if (hi) hi[i] = h;
+    lo[i] = l;
+  }
+}
 int blocks_for(long long n) { long long b = (n + 255) / 256; if (b > kNumSMs * 16) b = kNumSMs * 16; if (b < 1) b = 1; return (int)b; }
 }  // namespace
 
@@ -47,4 +56,13 @@ extern "C" int skd_round_tf32(long long n, const float* src, float* dst, cudaStr
   if (n <= 0) return 1;
   round_kernel<<<blocks_for(n), 256, 0, st>>>(n, src, dst);
   return finish("skd_round_tf32");
+}
+extern "C" int skd_split_tf32(long long n, const float* src, float* hi, float* lo, cudaStream_t st) {
+  // hi may be NULL: a TFLOAT32 tensor map rounds the original tensor to exactly that value on load, only lo must exist in memory
+  if (n % 4 || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15)) {
+    set_error_msg("skd_split_tf32", "n must be a multiple of 4 and the pointers 16-byte aligned"); return 0;
+  }
+  if (n <= 0) return 1;
+  split_kernel<<<blocks_for(n / 4), 256, 0, st>>>(n / 4, reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo));
+  return finish("skd_split_tf32");
 }

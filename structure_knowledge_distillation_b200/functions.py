@@ -104,13 +104,39 @@ def conv_forward_padded(x, weight, bias, stride, pad, dil, **epi):
     return y[:, :cout] if cout_p != cout else y, x
 
 
+def _small_cin(weight):
+    return weight.shape[1] <= 4 and weight.shape[2] * weight.shape[3] > 1
+
+
+def conv_forward_small_cin(x, weight, stride, pad, dil, precise=False, **epi):
+    """Tiny-Cin convolution (3-channel stem) as explicit im2col + one dense K=32 GEMM step on tcgen05."""
+    cout, cin, kh, kw = weight.shape
+    k = kh * kw * cin
+    kp = (k + 31) // 32 * 32
+    xin = x[:, :cin] if x.shape[1] != cin else x
+    col = ops.im2col_small(xin, kh, kw, stride, pad, dil, kp)
+    wp = torch.zeros((cout, 1, 1, kp), device=weight.device, dtype=torch.float32)
+    wp[:, 0, 0, :k] = ops.weight_ohwi(weight).reshape(cout, k)
+    if precise:
+        return ops.conv2d_fwd_3xtf32(col, wp, 1, 0, 1), col
+    return ops.conv2d_fwd(col, wp, 1, 0, 1, **epi), col
+
+
 class Conv2d(torch.autograd.Function):
     """nn.Conv2d forward / dgrad / wgrad on tcgen05.  x is NHWC-stored; weight is the (Cout,Cin,KH,KW) parameter held in
     channels-last (OHWI) storage."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, dil):
-        y, xin = conv_forward_padded(x, weight, bias, stride, pad, dil)
+    def forward(ctx, x, weight, bias, stride, pad, dil, precise=False):
+        ctx.small = _small_cin(weight) and bias is None and not x.requires_grad
+        if ctx.small:
+            y, xin = conv_forward_small_cin(x, weight, stride, pad, dil, precise=precise)
+        elif precise and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0 and ops.nhwc_meta(x)[4] == x.shape[1]:
+            # split-precision (3xTF32) forward for the layers whose rounding error train-mode BN amplifies most
+            xin = x
+            y = ops.conv2d_fwd_3xtf32(x, ops.weight_ohwi(weight), stride, pad, dil, shift=bias)
+        else:
+            y, xin = conv_forward_padded(x, weight, bias, stride, pad, dil)
         ctx.save_for_backward(xin, weight)
         ctx.cfg = (stride, pad, dil, bias is not None, tuple(x.shape))
         return y
@@ -122,6 +148,10 @@ class Conv2d(torch.autograd.Function):
         stride, pad, dil, has_bias, xshape = ctx.cfg
         w = ops.weight_ohwi(weight)
         cout, kh, kw, cin = w.shape
+        if ctx.small:                                        # xin is the im2col matrix: the weight gradient is a single-tap GEMM
+            dwc = ops.conv2d_wgrad(xin, ops.to_nhwc(dy), (1, 1), 1, 0, 1)               # [Cout][1][1][Kp]
+            dw = dwc.reshape(cout, -1)[:, :kh * kw * cin].reshape(cout, kh, kw, cin).permute(0, 3, 1, 2)
+            return None, dw, None, None, None, None, None
         cin_p, cout_p = ops.pad4(cin), ops.pad4(cout)
         dy = ops.pad_channels(dy, cout_p) if cout_p != cout else ops.to_nhwc(dy)
         if ops.nhwc_meta(dy)[4] % 4:
@@ -137,7 +167,7 @@ class Conv2d(torch.autograd.Function):
             dw = dw[:cout, :, :, :cin].permute(0, 3, 1, 2)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy)[:cout]
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class ABN(torch.autograd.Function):

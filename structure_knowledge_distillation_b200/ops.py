@@ -190,6 +190,38 @@ def conv2d_fwd(x, w_ohwi, stride, pad, dil, scale=None, shift=None, residual=Non
     return out
 
 
+def lo_tf32(t):
+    """dense tensor -> lo = rna_tf32(t - rna_tf32(t)), same layout (the hi part is what a TFLOAT32 tensor map makes of t itself)."""
+    lo = torch.empty_strided(t.shape, t.stride(), device=t.device, dtype=torch.float32)
+    lib().skd_split_tf32(t.numel(), _p(t), None, _p(lo), _st())
+    return lo
+
+
+def conv2d_fwd_3xtf32(x, w_ohwi, stride, pad, dil, shift=None):
+    """fp32-grade forward convolution: split-precision operands, three tensor-core passes in one launch."""
+    n, cin, h, w, ldx = nhwc_meta(x)
+    if ldx != cin:
+        raise ValueError("Non-contiguous input")
+    cout, kh, kw, _ = w_ohwi.shape
+    oh, ow = conv_out_hw(h, w, (kh, kw), stride, pad, dil)
+    out = empty_nhwc(n, cout, oh, ow, x.device)
+    log = CONV_EVENT_LOG
+    if log is not None:
+        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ev0.record()
+    xh, xl = x, lo_tf32(x)
+    wh, wl = w_ohwi, lo_tf32(w_ohwi)
+    if log is not None:
+        ev1.record()
+    lib().skd_conv2d_fwd_sm100_3xtf32(n, h, w, cin, cout, kh, kw, stride, pad, dil, _p(xh), _p(xl), ldx, _p(wh), _p(wl), _p(out), cout,
+                                      None, _p(shift), 0, 0.0, _st())
+    if log is not None:
+        ev2.record()
+        log.append((ev0, ev1, 0.0, ("split3x", n, cin, h, w, cout, kh, stride, dil)))
+        log.append((ev1, ev2, 3 * 2.0 * n * oh * ow * cout * cin * kh * kw, ("fwd3x", n, cin, h, w, cout, kh, stride, dil)))
+    return out
+
+
 def conv2d_dgrad(dy, w_ohwi, x_shape, stride, pad, dil, round_tf32=False, force_direct=False):
     """dx for y = conv(x, w).  stride 1: forward tcgen05 kernel on dy with the flipped/transposed weights."""
     n, cin, h, w = x_shape
@@ -260,6 +292,15 @@ def conv2d_wgrad(x, dy, kshape, stride, pad, dil, force_direct=False):
             ev1.record()
             log.append((ev0, ev1, 2.0 * n * doh * dow * cout * cin * kh * kw, ("wgrad", n, cin, h, w, cout, kh, stride, dil)))
     return dw
+
+
+def im2col_small(x, kh, kw, stride, pad, dil, kp):
+    """(N,Cin,H,W) NHWC-stored -> (N, kp, OH, OW) NHWC-stored im2col matrix (k = tap*Cin + ci, zero padded)."""
+    n, cin, h, w, ldx = nhwc_meta(x)
+    oh, ow = conv_out_hw(h, w, (kh, kw), stride, pad, dil)
+    col = empty_nhwc(n, kp, oh, ow, x.device)
+    lib().skd_im2col_small(n, h, w, cin, kh, kw, stride, pad, dil, _p(x), ldx, _p(col), kp, _st())
+    return col
 
 
 def colsum(dy):
