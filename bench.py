@@ -259,6 +259,7 @@ def run_ours(args, rank, local_rank, world):
         "data": "synthetic",
         "config": {"workload": "BASELINE.json configs[2]: ResNet18-PSP student + PSPNet-101 teacher, Pi+Pa+Ho (wgan-gp), batch 8/GPU at 512x1024, pool_scale 0.5",
                    "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d" % world,
+                   "precision": "fp32 storage; TF32 tensor-core operands (round-to-nearest by TMA), fp32 accumulate; student stem+layer1 forward in split-precision 3xTF32",
                    "cuda_graph": bool(use_graph), "launch_count_note": "gpu_launches = our kernels counted on an eager step x steps (graph replays re-issue the same launches)",
                    "l2": "per-step working set (activations ~10 GB) is far larger than the 126 MB L2: no flush needed"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": pin_i.numel() * 4 + pin_l.numel() * 8, "d2h_bytes_per_step": 4,
