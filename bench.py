@@ -91,6 +91,8 @@ def run_reference(args, rank, world):
         return
     import torch
     from oracle import cases, port
+    if args.ref_device == "cuda":
+        return run_reference_cuda(args)
     cores = _cpu_threads()
     torch.set_num_threads(cores)
     cfg = port.StepConfig(pi=True, pa=True, ho=True, adv_type="wgan-gp")
@@ -113,6 +115,40 @@ def run_reference(args, rank, world):
         "config": {"workload": "BASELINE.json configs[2]: ResNet18 student + PSPNet-101 teacher, Pi+Pa+Ho, 512x1024 (bounded sample: batch 1)"},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_reference_cuda(args):
+    """Not the contract's reference arm (that is the CPU leg above): the same restatement with its torch ops placed on cuda:0
+    -- cuDNN/cuBLAS eager, NCHW fp32, full batch 8 -- i.e. what the reference's stock code path costs on this box.  Printed as
+    context for the headline; `--ref-tf32 0` disables TF32 in cuDNN (torch's default allows it)."""
+    import torch
+    from oracle import cases, port
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True                                    # train_and_eval.py sets cudnn.benchmark
+    torch.backends.cudnn.allow_tf32 = bool(args.ref_tf32)
+    cfg = port.StepConfig(pi=True, pa=True, ho=True, adv_type="wgan-gp")
+    teacher, student, D = cases.build_models(seed=0, with_D=True)
+    teacher.to(dev); student.to(dev); D.to(dev)
+    g_opt, d_opt = port.make_optimizers(student, D, cfg)
+    images, labels = synthetic(BATCH_PER_GPU, 0)
+    images, labels = images.to(dev), labels.to(dev)
+    alpha = torch.rand(BATCH_PER_GPU, 1, 1, 1, device=dev)
+    steps, warm = args.steps, max(3, args.warmup)
+    for _ in range(warm):
+        port.distill_step(teacher, student, D, images, labels, cfg, g_opt, d_opt, gp_alpha=alpha)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        port.distill_step(teacher, student, D, images, labels, cfg, g_opt, d_opt, gp_alpha=alpha)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    print(json.dumps({
+        "impl": "reference", "device": "cuda (torch eager: cuDNN/cuBLAS, tf32 %s)" % ("allowed" if args.ref_tf32 else "off"),
+        "metric": METRIC, "value": BATCH_PER_GPU * 1e3 / ms, "unit": "images/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+        "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[2]: ResNet18 student + PSPNet-101 teacher, Pi+Pa+Ho, 512x1024, batch %d, inputs resident" % BATCH_PER_GPU},
+        "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
 
 
 def _cpu_threads():
@@ -286,6 +322,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cpu = the contract's arm; cuda = the same torch restatement on cuda:0 (context only)")
+    ap.add_argument("--ref-tf32", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-table", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly instead of replaying CUDA graphs")

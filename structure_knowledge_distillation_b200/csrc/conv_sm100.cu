@@ -52,6 +52,8 @@ struct ConvArgs {
   int passes;                      // 1: TF32;  3: split-precision 3xTF32 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32-grade result)
   int nstages;                     // pipeline stages in use (one fewer when the last stage buffer prefetches the residual)
   int res_prefetch;                // residual tiles are cp.async-prefetched one chunk ahead into the spare stage buffer
+  int reverse;                     // walk the tile list back to front (alternated per layer so a layer starts on the
+                                   // activations its producer wrote last, which are still in L2)
   int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
 };
 
@@ -111,7 +113,8 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        const int tl = a.reverse ? total_tiles - 1 - tile : tile;
+        const int mt = tl / a.n_tiles, nt = tl - mt * a.n_tiles;
         const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int iy0 = ty * a.BH * a.stride - a.pad, ix0 = tx * a.BW * a.stride - a.pad;
@@ -191,7 +194,8 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     uint8_t* resbuf = smem + (C::kStages - 1) * C::kStageBytes + group * C::kOutStageBytes;   // spare stage buffer (res_prefetch)
     auto prefetch_residual = [&](int t, int chunk) {
       if (t < total_tiles) {
-        const int mt_ = t / a.n_tiles, nt_ = t - mt_ * a.n_tiles;
+        const int tl_ = a.reverse ? total_tiles - 1 - t : t;
+        const int mt_ = tl_ / a.n_tiles, nt_ = tl_ - mt_ * a.n_tiles;
         const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
         const int ty_ = rem_ / a.tiles_x, tx_ = rem_ - ty_ * a.tiles_x;
         const int cc = nt_ * BLOCK_N + chunk * 32 + ck * 4;
@@ -209,7 +213,8 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     int pf_tile = -1, pf_chunk = -1;                               // what resbuf currently holds / is being filled with
     if (a.res_prefetch) { prefetch_residual(blockIdx.x, group); pf_tile = blockIdx.x; pf_chunk = group; }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int tl = a.reverse ? total_tiles - 1 - tile : tile;
+      const int mt = tl / a.n_tiles, nt = tl - mt * a.n_tiles;
       const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
       const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
       const int oy = ty * a.BH + dy, ox = tx * a.BW + dx;
@@ -389,6 +394,8 @@ EncodeIm2colFn get_encode_im2col() {
 }
 int g_conv_im2col = 1;
 int g_res_prefetch = 1;
+int g_tile_order = 0;             // 0 front-to-back, 1 back-to-front, 2 alternate per launch
+int g_tile_flip = 0;
 
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
@@ -455,6 +462,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
 
 extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
 extern "C" void skd_set_conv_res_prefetch(int on) { g_res_prefetch = on ? 1 : 0; }
+extern "C" void skd_set_conv_tile_order(int mode) { g_tile_order = mode; g_tile_flip = 0; }
 
 static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                          const float* x, const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, long long y_row, long long y_img, int oh_req,
@@ -534,6 +542,7 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     a.passes = 3;
   }
   CUtensorMap ty = tx;
+  a.reverse = (g_tile_order == 2) ? (g_tile_flip ^= 1) : g_tile_order;
   a.nstages = 0; a.res_prefetch = 0; a.sumsq = sumsq; a.no_store = no_store;
   a.tma_store = !no_store && (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) && (y_row % 4 == 0) && (y_img % 4 == 0);
   if (strided_out && (!a.tma_store || residual)) { set_error_msg(who, "strided output needs 16-byte aligned strides and no residual"); return 0; }
