@@ -57,23 +57,29 @@ struct ConvArgs {
   int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
 };
 
-template <int BLOCK_N>
+// PAIR = 1: one CTA per 128 x BLOCK_N tile (cta_group::1).
+// PAIR = 2: a cluster of two CTAs (one TPC) computes a 256 x BLOCK_N tile with cta_group::2 MMAs: each CTA stages its own 128
+//           pixels of A and only HALF of the weight tile, so the L2 -> shared-memory traffic per FLOP drops by a third (with fp32
+//           operands a 128 x 256 cta_group::1 tile needs ~62 B/clk/SM of fill bandwidth at full tensor rate -- the limiter).
+template <int BLOCK_N, int PAIR>
 struct Cfg {
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
+  static constexpr int kBBytes = (BLOCK_N / PAIR) * kBlockK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;       // power of two: 64..512
   static constexpr int kOutStageBytes = kBlockM * 32 * 4;                      // one 128-pixel x 32-channel chunk
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kOutStageBytes + 768 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4;
+  static constexpr int kFixedBytes = 2 * kOutStageBytes + 768 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4;
+  static constexpr int kFit = (232448 - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;                           // 4 / 6 / 8 / 8 (PAIR 1), 6 / 8 (PAIR 2)
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;       // power of two: 64..512
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_x2,
                       const __grid_constant__ CUtensorMap tmap_w2, const ConvArgs a) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, PAIR>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the pointer in the shared address space (integer round trips make nvcc emit generic LD/ST instead of LDS/STS)
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -88,22 +94,31 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   float* s_shift = s_scale + BLOCK_N;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // pair mode: rank 0 is the leader (issues the MMAs; owns the full / tmem_empty barriers both CTAs signal)
+  const uint32_t cta_rank = (PAIR == 2) ? ptx::cluster_ctarank() : 0u;
+  const int tile0 = (PAIR == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first tile of this CTA / CTA pair
+  const int tile_step = (PAIR == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_w);
     if (a.tma_store) ptx::prefetch_tmap(&tmap_y);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8 * PAIR); }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  if (warp == 1) {
+    if constexpr (PAIR == 2) ptx::tmem_alloc_2cta<C::kTmemCols>(tmem_base_slot);
+    else ptx::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  const int total_tiles = a.m_tiles * a.n_tiles;
+  // pair mode: a tile is two consecutive M tiles (this CTA's is 2*pm + rank; a ragged last one is a phantom that loads zeros)
+  const int m_units = (PAIR == 2) ? (a.m_tiles + 1) / 2 : a.m_tiles;
+  const int total_tiles = m_units * a.n_tiles;
   const int taps = a.KH * a.KW;
   const int k_iters = a.passes * taps * a.k_chunks;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
@@ -112,9 +127,11 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t full_bar0 = (PAIR == 2) ? ptx::mapa_shared(&full_bar[0], 0) : 0u;   // the leader's full barriers
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int tl = a.reverse ? total_tiles - 1 - tile : tile;
-        const int mt = tl / a.n_tiles, nt = tl - mt * a.n_tiles;
+        const int mu = tl / a.n_tiles, nt = tl - mu * a.n_tiles;
+        const int mt = (PAIR == 2) ? 2 * mu + (int)cta_rank : mu;
         const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int iy0 = ty * a.BH * a.stride - a.pad, ix0 = tx * a.BW * a.stride - a.pad;
@@ -136,12 +153,23 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * C::kStageBytes;
             uint8_t* sb = sa + kABytes;
-            ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-            if (a.im2col)
-              ptx::tma_load_im2col_4d(sa, mx, &full_bar[stage], kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
-            else
-              ptx::tma_load_4d(sa, mx, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
-            ptx::tma_load_3d(sb, mw, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
+            if constexpr (PAIR == 2) {
+              // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+              if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+              const uint32_t fb = full_bar0 + (uint32_t)stage * 8u;
+              if (a.im2col)
+                ptx::tma_load_im2col_4d_2cta(sa, mx, fb, kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
+              else
+                ptx::tma_load_4d_2cta(sa, mx, fb, kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
+              ptx::tma_load_3d_2cta(sb, mw, fb, kc * kBlockK, tap, nt * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+            } else {
+              ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+              if (a.im2col)
+                ptx::tma_load_im2col_4d(sa, mx, &full_bar[stage], kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
+              else
+                ptx::tma_load_4d(sa, mx, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
+              ptx::tma_load_3d(sb, mw, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
+            }
             if (++stage == a.nstages) { stage = 0; phase ^= 1; }
           }
         }
@@ -149,11 +177,11 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
+    // ===================== MMA issuer (pair mode: the leader CTA only) =====================
+    constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM * PAIR, BLOCK_N, 0, 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles && cta_rank == 0; tile += tile_step) {
       if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       __syncwarp();
       ptx::tc_fence_after();
@@ -168,10 +196,16 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
             const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * kUmmaK * 4, 16, 1024);
             const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * kUmmaK * 4, 16, 1024);
-            ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+            if constexpr (PAIR == 2) ptx::mma_tf32_2cta(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+            else ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
           }
-          ptx::mma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs retire
-          if (k == k_iters - 1) ptx::mma_commit(&tmem_full[acc]);
+          if constexpr (PAIR == 2) {                          // multicast: the stage / accumulator barriers of both CTAs
+            ptx::mma_commit_2cta(&empty_bar[stage]);
+            if (k == k_iters - 1) ptx::mma_commit_2cta(&tmem_full[acc]);
+          } else {
+            ptx::mma_commit(&empty_bar[stage]);               // smem stage reusable once these MMAs retire
+            if (k == k_iters - 1) ptx::mma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == a.nstages) { stage = 0; phase ^= 1; }
@@ -195,7 +229,8 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     auto prefetch_residual = [&](int t, int chunk) {
       if (t < total_tiles) {
         const int tl_ = a.reverse ? total_tiles - 1 - t : t;
-        const int mt_ = tl_ / a.n_tiles, nt_ = tl_ - mt_ * a.n_tiles;
+        const int mu_ = tl_ / a.n_tiles, nt_ = tl_ - mu_ * a.n_tiles;
+        const int mt_ = (PAIR == 2) ? 2 * mu_ + (int)cta_rank : mu_;
         const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
         const int ty_ = rem_ / a.tiles_x, tx_ = rem_ - ty_ * a.tiles_x;
         const int cc = nt_ * BLOCK_N + chunk * 32 + ck * 4;
@@ -203,7 +238,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 16 + (gt >> 3);
           const int roy = ty_ * a.BH + rr / a.BW, rox = tx_ * a.BW + rr % a.BW;
-          const bool ok = roy < a.OH && rox < a.OW && cc + 3 < a.Cout;
+          const bool ok = roy < a.OH && rox < a.OW && cc + 3 < a.Cout && mt_ < a.m_tiles;
           const float* src = ok ? a.residual + (((size_t)img_ * a.OH + roy) * a.OW + rox) * a.ldr + cc : a.residual;
           ptx::cp_async16(resbuf + rr * 128 + (ck << 4), src, ok ? 16 : 0);
         }
@@ -211,14 +246,16 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       ptx::cp_async_commit();
     };
     int pf_tile = -1, pf_chunk = -1;                               // what resbuf currently holds / is being filled with
-    if (a.res_prefetch) { prefetch_residual(blockIdx.x, group); pf_tile = blockIdx.x; pf_chunk = group; }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t tmem_empty0 = (PAIR == 2) ? ptx::mapa_shared(&tmem_empty[0], 0) : 0u;   // the leader's tmem_empty barriers
+    if (a.res_prefetch) { prefetch_residual(tile0, group); pf_tile = tile0; pf_chunk = group; }
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int tl = a.reverse ? total_tiles - 1 - tile : tile;
-      const int mt = tl / a.n_tiles, nt = tl - mt * a.n_tiles;
+      const int mu = tl / a.n_tiles, nt = tl - mu * a.n_tiles;
+      const int mt = (PAIR == 2) ? 2 * mu + (int)cta_rank : mu;
       const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
       const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
       const int oy = ty * a.BH + dy, ox = tx * a.BW + dx;
-      const bool valid = (oy < a.OH) && (ox < a.OW);
+      const bool valid = (oy < a.OH) && (ox < a.OW) && (mt < a.m_tiles);
       const size_t pix = ((size_t)img * a.OH + oy) * a.OW + ox;
       float* yrow = a.y + pix * a.ldy;
       const float* rrow = (a.residual && valid) ? a.residual + pix * a.ldr : nullptr;
@@ -250,7 +287,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int rr = i * 16 + (gt >> 3);
             const int roy = ty * a.BH + rr / a.BW, rox = tx * a.BW + rr % a.BW;
             q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (roy < a.OH && rox < a.OW && c0 + ck * 4 + 3 < a.Cout)
+            if (roy < a.OH && rox < a.OW && c0 + ck * 4 + 3 < a.Cout && mt < a.m_tiles)
               q[i] = __ldg(reinterpret_cast<const float4*>(a.residual + (((size_t)img * a.OH + roy) * a.OW + rox) * a.ldr + c0 + ck * 4));
           }
         }
@@ -336,7 +373,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           }
           if (a.res_prefetch) {                                                 // next chunk of this group: same tile or next tile
             int ntile = tile, nch = ch + 2;
-            if (nch >= BLOCK_N / 32 || nt * BLOCK_N + nch * 32 >= a.Cout) { ntile = tile + gridDim.x; nch = group; }
+            if (nch >= BLOCK_N / 32 || nt * BLOCK_N + nch * 32 >= a.Cout) { ntile = tile + tile_step; nch = group; }
             prefetch_residual(ntile, nch);
             pf_tile = ntile; pf_chunk = nch;
           }
@@ -355,7 +392,10 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR == 2) ptx::mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
+        else ptx::mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (is_store_leader) ptx::bulk_wait<0>();
@@ -366,8 +406,12 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<C::kTmemCols>(tmem_base); }
+  if constexpr (PAIR == 2) ptx::cluster_sync(); else __syncthreads();   // pair: the peer may still read this CTA's smem / signal its barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (PAIR == 2) ptx::tmem_dealloc_2cta<C::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -396,6 +440,7 @@ int g_conv_im2col = 1;
 int g_res_prefetch = 1;
 int g_tile_order = 0;             // 0 front-to-back, 1 back-to-front, 2 alternate per launch
 int g_tile_flip = 0;
+int g_cta_pairs = 0;              // 1: cta_group::2 pairs for BLOCK_N >= 128 when there are at least two M tiles
 
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
@@ -438,23 +483,37 @@ void pick_rect(int OH, int OW, int stride, int* BH, int* BW) {
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int PAIR>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx2, const CUtensorMap& tw2,
            const ConvArgs& a_in, cudaStream_t st) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, PAIR>;
   ConvArgs a = a_in;
   // residual epilogues on short-K convolutions: trade one pipeline stage for a cp.async residual prefetch buffer
   a.res_prefetch = (a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && C::kStageBytes >= 2 * C::kOutStageBytes && C::kStages >= 4;
   a.nstages = a.res_prefetch ? C::kStages - 1 : C::kStages;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_sm100_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_sm100_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("skd_conv2d_fwd_sm100(attr)", e); return 0; }
     attr = true;
   }
-  int grid = a.m_tiles * a.n_tiles;
-  if (grid > kNumSMs) grid = kNumSMs;
-  conv_fwd_sm100_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tx2, tw2, a);
+  if constexpr (PAIR == 2) {
+    // one cluster of two CTAs (the two SMs of a TPC) per 256-pixel tile; persistent over at most kNumSMs / 2 pairs
+    int pairs = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    if (pairs > kNumSMs / 2) pairs = kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fwd_sm100_kernel<BLOCK_N, PAIR>, tx, tw, ty, tx2, tw2, a);
+    if (e != cudaSuccess) { set_error("skd_conv2d_fwd_sm100(pair launch)", e); return 0; }
+  } else {
+    int grid = a.m_tiles * a.n_tiles;
+    if (grid > kNumSMs) grid = kNumSMs;
+    conv_fwd_sm100_kernel<BLOCK_N, PAIR><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tx2, tw2, a);
+  }
   return finish("skd_conv2d_fwd_sm100");
 }
 
@@ -463,6 +522,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
 extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
 extern "C" void skd_set_conv_res_prefetch(int on) { g_res_prefetch = on ? 1 : 0; }
 extern "C" void skd_set_conv_tile_order(int mode) { g_tile_order = mode; g_tile_flip = 0; }
+extern "C" void skd_set_conv_cta_pairs(int on) { g_cta_pairs = on ? 1 : 0; }
 
 static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                          const float* x, const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, long long y_row, long long y_img, int oh_req,
@@ -505,6 +565,7 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
              (!residual || ((ldr % 4 == 0) && !(reinterpret_cast<uintptr_t>(residual) & 15)));
   const int bn = Cout > 128 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
   a.n_tiles = (Cout + bn - 1) / bn;
+  const bool pair = g_cta_pairs && bn >= 128 && a.m_tiles >= 2;
 
   CUtensorMap tx, tw, tx2, tw2;
   auto encode_x = [&](CUtensorMap* m, const float* ptr) -> bool {
@@ -530,7 +591,7 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   auto encode_w = [&](CUtensorMap* m, const float* ptr) -> bool {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)(KH * KW), (cuuint64_t)Cout};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)KH * KW * Cin * 4};
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)bn};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)(pair ? bn / 2 : bn)};     // pair mode: each CTA stages half the rows
     cuuint32_t estr[3] = {1, 1, 1};
     return encode(m, 3, ptr, dims, strides, box, estr, who);
   };
@@ -554,11 +615,12 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode(&ty, 4, y, dims, strides, box, estr, who, true)) return 0;
   }
+  if (pair) return bn == 256 ? launch<256, 2>(tx, tw, ty, tx2, tw2, a, st) : launch<128, 2>(tx, tw, ty, tx2, tw2, a, st);
   switch (bn) {
-    case 256: return launch<256>(tx, tw, ty, tx2, tw2, a, st);
-    case 128: return launch<128>(tx, tw, ty, tx2, tw2, a, st);
-    case 64: return launch<64>(tx, tw, ty, tx2, tw2, a, st);
-    default: return launch<32>(tx, tw, ty, tx2, tw2, a, st);
+    case 256: return launch<256, 1>(tx, tw, ty, tx2, tw2, a, st);
+    case 128: return launch<128, 1>(tx, tw, ty, tx2, tw2, a, st);
+    case 64: return launch<64, 1>(tx, tw, ty, tx2, tw2, a, st);
+    default: return launch<32, 1>(tx, tw, ty, tx2, tw2, a, st);
   }
 }
 

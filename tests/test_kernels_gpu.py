@@ -288,6 +288,47 @@ def test_conv_residual_epilogue_prefetch(ops, N, Cin, H, W, Cout):
     lib().skd_set_conv_res_prefetch(1)
 
 
+PAIR_CASES = [
+    # N, Cin, H, W, Cout, k, stride, pad, dil, residual
+    (1, 128, 17, 19, 256, 3, 1, 2, 2, False),      # 3 M tiles: the last pair has a phantom second tile
+    (2, 128, 65, 129, 256, 1, 1, 0, 1, True),      # flat GEMM, residual prefetch chain, 132 M tiles
+    (3, 256, 10, 11, 1024, 1, 1, 0, 1, True),      # four N tiles
+    (2, 64, 33, 31, 128, 3, 2, 1, 1, False),       # BLOCK_N 128 pairs, stride 2
+    (2, 1024, 6, 7, 136, 3, 1, 1, 1, False),       # ragged Cout: the second CTA's weight half is mostly out of range
+    (1, 100, 20, 23, 72, 3, 1, 1, 1, True),        # Cout 72 -> BLOCK_N 128, second half holds 8 rows
+    (2, 256, 65, 129, 256, 3, 1, 2, 2, False),     # teacher layer3 conv2 shape (2 images)
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_fwd_cta_pairs(ops, case):
+    """cta_group::2 pairs (256 x N tiles, half the weight tile per CTA) against the single-CTA kernel and the fp64 reference."""
+    from structure_knowledge_distillation_b200._cabi import lib
+    N, Cin, H, W, Cout, k, s, p, d, with_res = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case[:9]))
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5
+    sc = torch.rand(Cout, device="cuda", generator=g) + 0.5; sh = torch.randn(Cout, device="cuda", generator=g)
+    ref = _conv_ref64(x, w, s, p, d) * sc.double()[None, :, None, None] + sh.double()[None, :, None, None]
+    res = None
+    if with_res:
+        res = ops.to_nhwc(torch.randn(ref.shape, device="cuda", generator=g)); ref = ref + res.double()
+    ref = torch.relu(ref)
+    xc = ops.to_nhwc(x); wo = ops.weight_ohwi(w)
+    try:
+        for im2col in (1, 0):
+            lib().skd_set_conv_im2col(im2col)
+            lib().skd_set_conv_cta_pairs(0)
+            y1 = ops.conv2d_fwd(xc, wo, s, p, d, scale=sc, shift=sh, residual=res, act="relu")
+            lib().skd_set_conv_cta_pairs(1)
+            y2 = ops.conv2d_fwd(xc, wo, s, p, d, scale=sc, shift=sh, residual=res, act="relu")
+            torch.cuda.synchronize()
+            assert rel(y2, ref) < 2e-3, ("pair vs fp64", im2col, rel(y2, ref))
+            assert rel(y2, y1) < 1e-6, ("pair vs single CTA", im2col, rel(y2, y1))
+    finally:
+        lib().skd_set_conv_cta_pairs(0); lib().skd_set_conv_im2col(1)
+
+
 def test_conv_fwd_epilogue_and_pitch(ops):
     """folded-BN scale/shift + residual + ReLU, reading a channel slice and writing into a slice of a wider buffer."""
     g = torch.Generator(device="cuda").manual_seed(7)

@@ -1,0 +1,43 @@
+"""Teacher / student conv shapes of the 512x1024 step: single-CTA tiles vs cta_group::2 pairs (skd_set_conv_cta_pairs)."""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from structure_knowledge_distillation_b200 import ops, _cabi
+L = _cabi.lib()
+SHAPES = [  # name, N, Cin, H, W, Cout, k, stride, pad, dil, residual
+    ("t.layer3 conv1 1x1 1024->256", 8, 1024, 65, 129, 256, 1, 1, 0, 1, False),
+    ("t.layer3 conv2 3x3 256->256 d2", 8, 256, 65, 129, 256, 3, 1, 2, 2, False),
+    ("t.layer3 conv3 1x1 256->1024 +res", 8, 256, 65, 129, 1024, 1, 1, 0, 1, True),
+    ("t.layer4 conv1 1x1 2048->512", 8, 2048, 65, 129, 512, 1, 1, 0, 1, False),
+    ("t.layer4 conv2 3x3 512->512 d4", 8, 512, 65, 129, 512, 3, 1, 4, 4, False),
+    ("t.layer4 conv3 1x1 512->2048 +res", 8, 512, 65, 129, 2048, 1, 1, 0, 1, True),
+    ("t.layer2 conv2 3x3 128->128", 8, 128, 65, 129, 128, 3, 1, 1, 1, False),
+    ("t.layer1 conv3 1x1 64->256 +res", 8, 64, 129, 257, 256, 1, 1, 0, 1, True),
+    ("t.psp bottleneck 3x3 4096->512", 8, 4096, 65, 129, 512, 3, 1, 1, 1, False),
+    ("s.layer3 3x3 256->256 d2", 8, 256, 65, 129, 256, 3, 1, 2, 2, False),
+    ("s.layer4 3x3 512->512 d4", 8, 512, 65, 129, 512, 3, 1, 4, 4, False),
+]
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+def timeit(fn, reps=10):
+    fn(); fn(); torch.cuda.synchronize(); s.record()
+    for _ in range(reps): fn()
+    e.record(); torch.cuda.synchronize(); return s.elapsed_time(e) / reps
+g = torch.Generator(device="cuda").manual_seed(0)
+for name, N, Cin, H, W, Cout, k, st, p, d, with_res in SHAPES:
+    x = ops.to_nhwc(torch.randn(N, Cin, H, W, device="cuda", generator=g))
+    w = ops.weight_ohwi(torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5)
+    OH = (H + 2 * p - d * (k - 1) - 1) // st + 1; OW = (W + 2 * p - d * (k - 1) - 1) // st + 1
+    res = ops.to_nhwc(torch.randn(N, Cout, OH, OW, device="cuda", generator=g)) if with_res else None
+    sc = torch.rand(Cout, device="cuda", generator=g) + 0.5; sh = torch.randn(Cout, device="cuda", generator=g)
+    out = ops.to_nhwc(torch.empty(N, Cout, OH, OW, device="cuda"))
+    fl = 2.0 * N * OH * OW * Cout * Cin * k * k
+    row = []
+    ys = []
+    for pairs in (0, 1):
+        L.skd_set_conv_cta_pairs(pairs)
+        t = timeit(lambda: ops.conv2d_fwd(x, w, st, p, d, scale=sc, shift=sh, residual=res, act="relu", out=out))
+        ys.append(out.clone())
+        row.append((t, fl / t / 1e9))
+    L.skd_set_conv_cta_pairs(0)
+    diff = (ys[0] - ys[1]).abs().max().item()
+    print("%-36s single %.3f ms %6.1f TF | pairs %.3f ms %6.1f TF | x%.2f | max diff %.2g" % (name, row[0][0], row[0][1], row[1][0], row[1][1], row[0][0] / row[1][0], diff), flush=True)
