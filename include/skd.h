@@ -151,10 +151,11 @@ int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w,
 int skd_round_tf32(long long n, const float* src, float* dst, cudaStream_t);
 void skd_set_tf32_tma_type(int use_tfloat32_type);
 void skd_set_wgrad_linear(int on);     /* 1 (default): wgrad K-blocks are 32 consecutive pixels (im2col TMA); 0: 4x8 rectangles */
-void skd_set_conv_res_prefetch(int on); /* 1 (default): residual tiles prefetched with cp.async into a spare pipeline stage */
+void skd_set_conv_res_prefetch(int on); /* 1 (default): residual tiles arrive through a TMA ring in spare pipeline-stage buffers */
 void skd_set_conv_tile_order(int mode); /* 0 (default) front-to-back, 1 back-to-front, 2 alternate per launch (a consumer starts on
                                           the tail its producer left in L2) */
-void skd_set_conv_cta_pairs(int on);   /* 1: 256 x N tiles on CTA pairs (tcgen05 cta_group::2, half the weight tile per CTA); 0 (default) */
+void skd_set_conv_cta_pairs(int mode); /* 0: single-CTA tiles only; 1 (default): 256 x N tiles on CTA pairs (tcgen05 cta_group::2, half the
+                                          weight tile per CTA) where measured faster; 3: pairs wherever possible (tests) */
 void skd_set_conv_im2col(int on);      /* 1 (default): TMA im2col-mode M tiles for k>1 / strided convs; 0: rectangular tiled-mode tiles */
 
 /* ---- E. pooling / resampling / optimiser ---- */

@@ -35,6 +35,7 @@ constexpr int kBlockK = 32;                 // fp32 elements = 128 B = one swizz
 constexpr int kUmmaK = 8;                   // tf32
 constexpr int kThreads = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kABytes = kBlockM * kBlockK * 4;
+constexpr int kResSlots = 3;                // residual ring depth per epilogue group: two loads in flight while one is consumed
 
 struct ConvArgs {
   int N, OH, OW, Cout, Cin;
@@ -50,8 +51,8 @@ struct ConvArgs {
   double* sumsq;                   // optional: += sum of squares of every valid output element (fused L2 reduction)
   int no_store;                    // 1: the output tensor is not written at all (reduction-only epilogue)
   int passes;                      // 1: TF32;  3: split-precision 3xTF32 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32-grade result)
-  int nstages;                     // pipeline stages in use (one fewer when the last stage buffer prefetches the residual)
-  int res_prefetch;                // residual tiles are cp.async-prefetched one chunk ahead into the spare stage buffer
+  int nstages;                     // A/B pipeline stages in use (the residual ring takes over the buffers of the others)
+  int res_prefetch;                // residual tiles arrive through a TMA ring (kResSlots 16 KB slots per epilogue group)
   int reverse;                     // walk the tile list back to front (alternated per layer so a layer starts on the
                                    // activations its producer wrote last, which are still in L2)
   int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
@@ -78,7 +79,7 @@ template <int BLOCK_N, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_x2,
-                      const __grid_constant__ CUtensorMap tmap_w2, const ConvArgs a) {
+                      const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_r, const ConvArgs a) {
   using C = Cfg<BLOCK_N, PAIR>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the pointer in the shared address space (integer round trips make nvcc emit generic LD/ST instead of LDS/STS)
@@ -90,6 +91,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(tmem_base_slot + 2);                  // [2 groups][kResSlots]
   float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [BLOCK_N], 16B aligned
   float* s_shift = s_scale + BLOCK_N;
 
@@ -105,6 +107,8 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (a.tma_store) ptx::prefetch_tmap(&tmap_y);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8 * PAIR); }
+    for (int s = 0; s < 2 * kResSlots; ++s) ptx::mbar_init(&res_full[s], 1);
+    if (a.res_prefetch) ptx::prefetch_tmap(&tmap_r);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -225,29 +229,35 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     int acc = 0; uint32_t acc_phase = 0;
     double sq_acc = 0.0;
     const int gt = (ew & 3) * 32 + lane, ck = gt & 7;            // coalesced mapping: 8 threads per 128-byte pixel row
-    uint8_t* resbuf = smem + (C::kStages - 1) * C::kStageBytes + group * C::kOutStageBytes;   // spare stage buffer (res_prefetch)
-    auto prefetch_residual = [&](int t, int chunk) {
-      if (t < total_tiles) {
-        const int tl_ = a.reverse ? total_tiles - 1 - t : t;
-        const int mu_ = tl_ / a.n_tiles, nt_ = tl_ - mu_ * a.n_tiles;
-        const int mt_ = (PAIR == 2) ? 2 * mu_ + (int)cta_rank : mu_;
-        const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
-        const int ty_ = rem_ / a.tiles_x, tx_ = rem_ - ty_ * a.tiles_x;
-        const int cc = nt_ * BLOCK_N + chunk * 32 + ck * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 16 + (gt >> 3);
-          const int roy = ty_ * a.BH + rr / a.BW, rox = tx_ * a.BW + rr % a.BW;
-          const bool ok = roy < a.OH && rox < a.OW && cc + 3 < a.Cout && mt_ < a.m_tiles;
-          const float* src = ok ? a.residual + (((size_t)img_ * a.OH + roy) * a.OW + rox) * a.ldr + cc : a.residual;
-          ptx::cp_async16(resbuf + rr * 128 + (ck << 4), src, ok ? 16 : 0);
-        }
-      }
-      ptx::cp_async_commit();
+    // residual ring (res_prefetch): the group's store leader TMA-loads the BH x BW x 32ch residual box of the chunks this group
+    // will process, kResSlots - 1 chunks ahead, into the buffers of the unused pipeline stages (same 128B-swizzled layout as the
+    // output staging tile).  Deep, asynchronous and issued by one thread: the epilogue warps never wait on global memory.
+    uint8_t* ring = smem + a.nstages * C::kStageBytes + group * (kResSlots * C::kOutStageBytes);
+    uint64_t* rfull = res_full + group * kResSlots;
+    auto chunk_valid = [&](int t, int c) -> bool {
+      const int tl_ = a.reverse ? total_tiles - 1 - t : t;
+      const int nt_ = tl_ % a.n_tiles;
+      return c < BLOCK_N / 32 && nt_ * BLOCK_N + c * 32 < a.Cout;
     };
-    int pf_tile = -1, pf_chunk = -1;                               // what resbuf currently holds / is being filled with
+    auto seek = [&](int& t, int& c) {                               // first (tile, chunk) of this group at or after (t, c)
+      while (t < total_tiles && !chunk_valid(t, c)) { t += tile_step; c = group; }
+    };
+    auto issue_residual = [&](int t, int c, int slot) {
+      const int tl_ = a.reverse ? total_tiles - 1 - t : t;
+      const int mu_ = tl_ / a.n_tiles, nt_ = tl_ - mu_ * a.n_tiles;
+      const int mt_ = (PAIR == 2) ? 2 * mu_ + (int)cta_rank : mu_;
+      const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
+      const int ty_ = rem_ / a.tiles_x, tx_ = rem_ - ty_ * a.tiles_x;
+      ptx::mbar_expect_tx(&rfull[slot], C::kOutStageBytes);
+      ptx::tma_load_4d(ring + slot * C::kOutStageBytes, &tmap_r, &rfull[slot], nt_ * BLOCK_N + c * 32, tx_ * a.BW, ty_ * a.BH, img_);
+    };
+    int p_tile = total_tiles, p_ch = group;                          // next chunk to request (store leader only)
+    if (a.res_prefetch && is_store_leader) {
+      p_tile = tile0; seek(p_tile, p_ch);
+      for (int i = 0; i < kResSlots && p_tile < total_tiles; ++i) { issue_residual(p_tile, p_ch, i); p_ch += 2; seek(p_tile, p_ch); }
+    }
+    int r_slot = 0; uint32_t r_phase = 0;                            // ring slot / parity of the chunk being consumed
     const uint32_t tmem_empty0 = (PAIR == 2) ? ptx::mapa_shared(&tmem_empty[0], 0) : 0u;   // the leader's tmem_empty barriers
-    if (a.res_prefetch) { prefetch_residual(tile0, group); pf_tile = tile0; pf_chunk = group; }
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int tl = a.reverse ? total_tiles - 1 - tile : tile;
       const int mu = tl / a.n_tiles, nt = tl - mu * a.n_tiles;
@@ -345,10 +355,13 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             // residual add + activation on the staged tile (residual registers were loaded coalesced above)
             ptx::named_bar_sync(1 + group, 128);
             if (a.res_prefetch) {
-              if (pf_tile != tile || pf_chunk != ch) prefetch_residual(tile, ch);   // chain broken (ragged Cout): fetch now
-              ptx::cp_async_wait_all();                                         // this thread's own 8 x 16 B have landed
+              ptx::mbar_wait(&rfull[r_slot], r_phase);                          // this chunk's residual box has landed
+              const uint8_t* rs = ring + r_slot * C::kOutStageBytes;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) q[i] = *reinterpret_cast<const float4*>(resbuf + (i * 16 + (gt >> 3)) * 128 + (ck << 4));
+              for (int i = 0; i < 8; ++i) {
+                const int rr = i * 16 + (gt >> 3);
+                q[i] = *reinterpret_cast<const float4*>(rs + rr * 128 + ((ck ^ (rr & 7)) << 4));
+              }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -371,11 +384,10 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             ptx::tma_store_4d(&tmap_y, stg, c0, tx * a.BW, ty * a.BH, img);
             ptx::bulk_commit();
           }
-          if (a.res_prefetch) {                                                 // next chunk of this group: same tile or next tile
-            int ntile = tile, nch = ch + 2;
-            if (nch >= BLOCK_N / 32 || nt * BLOCK_N + nch * 32 >= a.Cout) { ntile = tile + tile_step; nch = group; }
-            prefetch_residual(ntile, nch);
-            pf_tile = ntile; pf_chunk = nch;
+          if (a.res_prefetch) {
+            // every thread of the group has read the slot (barrier above, after its proxy fence): refill it
+            if (is_store_leader && p_tile < total_tiles) { issue_residual(p_tile, p_ch, r_slot); p_ch += 2; seek(p_tile, p_ch); }
+            if (++r_slot == kResSlots) { r_slot = 0; r_phase ^= 1; }
           }
         } else if (valid) {
 #pragma unroll
@@ -440,7 +452,7 @@ int g_conv_im2col = 1;
 int g_res_prefetch = 1;
 int g_tile_order = 0;             // 0 front-to-back, 1 back-to-front, 2 alternate per launch
 int g_tile_flip = 0;
-int g_cta_pairs = 0;              // 1: cta_group::2 pairs for BLOCK_N >= 128 when there are at least two M tiles
+int g_cta_pairs = 1;              // 0: never; 1: cta_group::2 pairs where they measured faster; 2|3: wherever they are possible
 
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
@@ -485,12 +497,14 @@ void pick_rect(int OH, int OW, int stride, int* BH, int* BW) {
 
 template <int BLOCK_N, int PAIR>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx2, const CUtensorMap& tw2,
-           const ConvArgs& a_in, cudaStream_t st) {
+           const CUtensorMap& tr, const ConvArgs& a_in, cudaStream_t st) {
   using C = Cfg<BLOCK_N, PAIR>;
   ConvArgs a = a_in;
-  // residual epilogues on short-K convolutions: trade one pipeline stage for a cp.async residual prefetch buffer
-  a.res_prefetch = (a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && C::kStageBytes >= 2 * C::kOutStageBytes && C::kStages >= 4;
-  a.nstages = a.res_prefetch ? C::kStages - 1 : C::kStages;
+  // residual epilogues are HBM-bound: trade A/B pipeline depth for the residual TMA ring (2 groups x kResSlots x 16 KB)
+  constexpr int kRingBytes = 2 * kResSlots * C::kOutStageBytes;
+  constexpr int kFreed = (kRingBytes + C::kStageBytes - 1) / C::kStageBytes;
+  a.res_prefetch = (a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && (C::kStages - kFreed >= 2);
+  a.nstages = a.res_prefetch ? C::kStages - kFreed : C::kStages;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_sm100_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -507,12 +521,12 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fwd_sm100_kernel<BLOCK_N, PAIR>, tx, tw, ty, tx2, tw2, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fwd_sm100_kernel<BLOCK_N, PAIR>, tx, tw, ty, tx2, tw2, tr, a);
     if (e != cudaSuccess) { set_error("skd_conv2d_fwd_sm100(pair launch)", e); return 0; }
   } else {
     int grid = a.m_tiles * a.n_tiles;
     if (grid > kNumSMs) grid = kNumSMs;
-    conv_fwd_sm100_kernel<BLOCK_N, PAIR><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tx2, tw2, a);
+    conv_fwd_sm100_kernel<BLOCK_N, PAIR><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tx2, tw2, tr, a);
   }
   return finish("skd_conv2d_fwd_sm100");
 }
@@ -522,7 +536,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
 extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
 extern "C" void skd_set_conv_res_prefetch(int on) { g_res_prefetch = on ? 1 : 0; }
 extern "C" void skd_set_conv_tile_order(int mode) { g_tile_order = mode; g_tile_flip = 0; }
-extern "C" void skd_set_conv_cta_pairs(int on) { g_cta_pairs = on ? 1 : 0; }
+extern "C" void skd_set_conv_cta_pairs(int mode) { g_cta_pairs = mode & 3; }
 
 static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                          const float* x, const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, long long y_row, long long y_img, int oh_req,
@@ -565,7 +579,10 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
              (!residual || ((ldr % 4 == 0) && !(reinterpret_cast<uintptr_t>(residual) & 15)));
   const int bn = Cout > 128 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
   a.n_tiles = (Cout + bn - 1) / bn;
-  const bool pair = g_cta_pairs && bn >= 128 && a.m_tiles >= 2;
+  // CTA pairs (measured, tools/pair_bench.py): +5-11% on the 256-wide non-residual tiles; with a fused residual only when the K loop
+  // is long enough (>= 16 chunks) that the two A/B stages the residual ring leaves a single CTA become the limiter
+  const bool pair_ok = bn >= 128 && a.m_tiles >= 2;
+  const bool pair = pair_ok && ((g_cta_pairs & 2) ? true : (g_cta_pairs & 1) ? (bn == 256 && (!residual || Cin * KH * KW >= 512)) : false);
 
   CUtensorMap tx, tw, tx2, tw2;
   auto encode_x = [&](CUtensorMap* m, const float* ptr) -> bool {
@@ -615,12 +632,20 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode(&ty, 4, y, dims, strides, box, estr, who, true)) return 0;
   }
-  if (pair) return bn == 256 ? launch<256, 2>(tx, tw, ty, tx2, tw2, a, st) : launch<128, 2>(tx, tw, ty, tx2, tw2, a, st);
+  CUtensorMap tr = ty;                                          // residual boxes: same geometry as the output boxes, own pitch
+  if (a.tma_store && residual && a.vec_ok) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldr * 4, (cuuint64_t)a.OW * ldr * 4, (cuuint64_t)a.OH * a.OW * ldr * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode(&tr, 4, residual, dims, strides, box, estr, who, true)) return 0;      // plain FLOAT32: the residual is not rounded
+  }
+  if (pair) return bn == 256 ? launch<256, 2>(tx, tw, ty, tx2, tw2, tr, a, st) : launch<128, 2>(tx, tw, ty, tx2, tw2, tr, a, st);
   switch (bn) {
-    case 256: return launch<256, 1>(tx, tw, ty, tx2, tw2, a, st);
-    case 128: return launch<128, 1>(tx, tw, ty, tx2, tw2, a, st);
-    case 64: return launch<64, 1>(tx, tw, ty, tx2, tw2, a, st);
-    default: return launch<32, 1>(tx, tw, ty, tx2, tw2, a, st);
+    case 256: return launch<256, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
+    case 128: return launch<128, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
+    case 64: return launch<64, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
+    default: return launch<32, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
   }
 }
 

@@ -320,13 +320,13 @@ def test_conv_fwd_cta_pairs(ops, case):
             lib().skd_set_conv_im2col(im2col)
             lib().skd_set_conv_cta_pairs(0)
             y1 = ops.conv2d_fwd(xc, wo, s, p, d, scale=sc, shift=sh, residual=res, act="relu")
-            lib().skd_set_conv_cta_pairs(1)
+            lib().skd_set_conv_cta_pairs(3)
             y2 = ops.conv2d_fwd(xc, wo, s, p, d, scale=sc, shift=sh, residual=res, act="relu")
             torch.cuda.synchronize()
             assert rel(y2, ref) < 2e-3, ("pair vs fp64", im2col, rel(y2, ref))
             assert rel(y2, y1) < 1e-6, ("pair vs single CTA", im2col, rel(y2, y1))
     finally:
-        lib().skd_set_conv_cta_pairs(0); lib().skd_set_conv_im2col(1)
+        lib().skd_set_conv_cta_pairs(1); lib().skd_set_conv_im2col(1)
 
 
 def test_conv_fwd_epilogue_and_pitch(ops):

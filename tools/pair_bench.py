@@ -31,13 +31,12 @@ for name, N, Cin, H, W, Cout, k, st, p, d, with_res in SHAPES:
     sc = torch.rand(Cout, device="cuda", generator=g) + 0.5; sh = torch.randn(Cout, device="cuda", generator=g)
     out = ops.to_nhwc(torch.empty(N, Cout, OH, OW, device="cuda"))
     fl = 2.0 * N * OH * OW * Cout * Cin * k * k
-    row = []
-    ys = []
-    for pairs in (0, 1):
-        L.skd_set_conv_cta_pairs(pairs)
+    ys, cols = [], []
+    for pairs, ring in ((0, 1), (3, 1)) + (((0, 0), (3, 0)) if with_res else ()):
+        L.skd_set_conv_cta_pairs(pairs); L.skd_set_conv_res_prefetch(ring)
         t = timeit(lambda: ops.conv2d_fwd(x, w, st, p, d, scale=sc, shift=sh, residual=res, act="relu", out=out))
         ys.append(out.clone())
-        row.append((t, fl / t / 1e9))
-    L.skd_set_conv_cta_pairs(0)
-    diff = (ys[0] - ys[1]).abs().max().item()
-    print("%-36s single %.3f ms %6.1f TF | pairs %.3f ms %6.1f TF | x%.2f | max diff %.2g" % (name, row[0][0], row[0][1], row[1][0], row[1][1], row[0][0] / row[1][0], diff), flush=True)
+        cols.append("%s%s %.3f ms %5.1f TF" % ("pair" if pairs else "single", "" if ring else "/noring", t, fl / t / 1e9))
+    L.skd_set_conv_cta_pairs(1); L.skd_set_conv_res_prefetch(1)
+    diff = max((ys[0] - y).abs().max().item() for y in ys[1:])
+    print("%-34s %s | max diff %.2g" % (name, " | ".join(cols), diff), flush=True)
