@@ -156,6 +156,7 @@ void skd_set_conv_tile_order(int mode); /* 0 (default) front-to-back, 1 back-to-
                                           the tail its producer left in L2) */
 void skd_set_conv_cta_pairs(int mode); /* 0: single-CTA tiles only; 1 (default): 256 x N tiles on CTA pairs (tcgen05 cta_group::2, half the
                                           weight tile per CTA) where measured faster; 3: pairs wherever possible (tests) */
+void skd_set_conv_k_order(int mode);   /* K loop of k>1 convolutions: 0 (default) by working set, 1 taps outermost, 2 channel chunks outermost */
 void skd_set_conv_im2col(int on);      /* 1 (default): TMA im2col-mode M tiles for k>1 / strided convs; 0: rectangular tiled-mode tiles */
 
 /* ---- E. pooling / resampling / optimiser ---- */

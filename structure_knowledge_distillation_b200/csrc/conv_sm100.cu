@@ -53,6 +53,7 @@ struct ConvArgs {
   int passes;                      // 1: TF32;  3: split-precision 3xTF32 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32-grade result)
   int nstages;                     // A/B pipeline stages in use (the residual ring takes over the buffers of the others)
   int res_prefetch;                // residual tiles arrive through a TMA ring (kResSlots 16 KB slots per epilogue group)
+  int kc_outer;                    // K loop order: 1 = channel chunk outermost / taps innermost, 0 = taps outermost
   int reverse;                     // walk the tile list back to front (alternated per layer so a layer starts on the
                                    // activations its producer wrote last, which are still in L2)
   int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
@@ -124,7 +125,10 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const int m_units = (PAIR == 2) ? (a.m_tiles + 1) / 2 : a.m_tiles;
   const int total_tiles = m_units * a.n_tiles;
   const int taps = a.KH * a.KW;
-  const int k_iters = a.passes * taps * a.k_chunks;
+  const int k_iters = taps * a.k_chunks;
+  // split-precision (passes == 3): a stage holds {x_hi, w_hi, x_lo, w_lo} tiles and every K step issues hi*hi + lo*hi + hi*lo
+  const bool split3 = (a.passes == 3);
+  const int stage_stride = split3 ? 2 * C::kStageBytes : C::kStageBytes;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   if (warp == 0) {
@@ -148,35 +152,48 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           ip0 = (r2 / a.rOW) * a.stride - a.pad;
           iq0 = (r2 % a.rOW) * a.stride - a.pad;
         }
-        for (int pass = 0; pass < a.passes; ++pass) {
-        const CUtensorMap* mx = (pass == 1) ? &tmap_x2 : &tmap_x;      // pass 1 reads the low part of x, pass 2 the low part of w
-        const CUtensorMap* mw = (pass == 2) ? &tmap_w2 : &tmap_w;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int kh = tap / a.KW, kw = tap - kh * a.KW;
-          for (int kc = 0; kc < a.k_chunks; ++kc) {
+        // kc_outer: channel chunk outermost, filter taps innermost -- the taps of one chunk re-read (shifted) the same input lines,
+        // L2 hits whatever Cin is.  Taps outermost streams Cin * 128 pixels * 148 CTAs between reuses (310 MB at Cin = 4096, far
+        // beyond L2: 679 -> 748 TFLOP/s on the PSP bottleneck) but measured ~5% faster while that working set still fits.
+        const int n_outer = a.kc_outer ? a.k_chunks : taps, n_inner = a.kc_outer ? taps : a.k_chunks;
+        for (int io = 0; io < n_outer; ++io) {
+          for (int ii = 0; ii < n_inner; ++ii) {
+            const int kc = a.kc_outer ? io : ii, tap = a.kc_outer ? ii : io;
+            const int kh = tap / a.KW, kw = tap - kh * a.KW;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * C::kStageBytes;
+            uint8_t* sa = smem + stage * stage_stride;
             uint8_t* sb = sa + kABytes;
+            const uint32_t bytes = (uint32_t)stage_stride;
             if constexpr (PAIR == 2) {
               // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
-              if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+              if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * bytes);
               const uint32_t fb = full_bar0 + (uint32_t)stage * 8u;
-              if (a.im2col)
-                ptx::tma_load_im2col_4d_2cta(sa, mx, fb, kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
-              else
-                ptx::tma_load_4d_2cta(sa, mx, fb, kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
-              ptx::tma_load_3d_2cta(sb, mw, fb, kc * kBlockK, tap, nt * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+              const int wrow = nt * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);
+              for (int part = 0; part < (split3 ? 2 : 1); ++part) {
+                const CUtensorMap* mx = part ? &tmap_x2 : &tmap_x;
+                const CUtensorMap* mw = part ? &tmap_w2 : &tmap_w;
+                uint8_t* pa = sa + part * C::kStageBytes; uint8_t* pb = sb + part * C::kStageBytes;
+                if (a.im2col)
+                  ptx::tma_load_im2col_4d_2cta(pa, mx, fb, kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
+                else
+                  ptx::tma_load_4d_2cta(pa, mx, fb, kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
+                ptx::tma_load_3d_2cta(pb, mw, fb, kc * kBlockK, tap, wrow);
+              }
             } else {
-              ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-              if (a.im2col)
-                ptx::tma_load_im2col_4d(sa, mx, &full_bar[stage], kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
-              else
-                ptx::tma_load_4d(sa, mx, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
-              ptx::tma_load_3d(sb, mw, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
+              ptx::mbar_expect_tx(&full_bar[stage], bytes);
+              for (int part = 0; part < (split3 ? 2 : 1); ++part) {
+                const CUtensorMap* mx = part ? &tmap_x2 : &tmap_x;
+                const CUtensorMap* mw = part ? &tmap_w2 : &tmap_w;
+                uint8_t* pa = sa + part * C::kStageBytes; uint8_t* pb = sb + part * C::kStageBytes;
+                if (a.im2col)
+                  ptx::tma_load_im2col_4d(pa, mx, &full_bar[stage], kc * kBlockK, iq0, ip0, in0, (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
+                else
+                  ptx::tma_load_4d(pa, mx, &full_bar[stage], kc * kBlockK, ix0 + kw * a.dil, iy0 + kh * a.dil, img);
+                ptx::tma_load_3d(pb, mw, &full_bar[stage], kc * kBlockK, tap, nt * BLOCK_N);
+              }
             }
             if (++stage == a.nstages) { stage = 0; phase ^= 1; }
           }
-        }
         }
       }
     }
@@ -194,14 +211,21 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         if (lane == 0) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sa = ptx::smem_u32(smem + stage * stage_stride);
           const uint32_t sb = sa + kABytes;
+          auto mma = [&](uint64_t da, uint64_t db, uint32_t accumulate) {
+            if constexpr (PAIR == 2) ptx::mma_tf32_2cta(tmem_d, da, db, idesc, accumulate);
+            else ptx::mma_tf32(tmem_d, da, db, idesc, accumulate);
+          };
 #pragma unroll
           for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
             const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * kUmmaK * 4, 16, 1024);
             const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * kUmmaK * 4, 16, 1024);
-            if constexpr (PAIR == 2) ptx::mma_tf32_2cta(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
-            else ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+            mma(da, db, (k | kk) != 0 ? 1u : 0u);
+            if (split3) {                                       // + x_lo * w_hi + x_hi * w_lo (the lo tiles sit kStageBytes further)
+              mma(ptx::make_smem_desc_sw128(sa + C::kStageBytes + kk * kUmmaK * 4, 16, 1024), db, 1u);
+              mma(da, ptx::make_smem_desc_sw128(sb + C::kStageBytes + kk * kUmmaK * 4, 16, 1024), 1u);
+            }
           }
           if constexpr (PAIR == 2) {                          // multicast: the stage / accumulator barriers of both CTAs
             ptx::mma_commit_2cta(&empty_bar[stage]);
@@ -452,6 +476,7 @@ int g_conv_im2col = 1;
 int g_res_prefetch = 1;
 int g_tile_order = 0;             // 0 front-to-back, 1 back-to-front, 2 alternate per launch
 int g_tile_flip = 0;
+int g_k_order = 0;                // 0: by working set (channel chunks outermost when Cin >= 2048); 1: taps outermost; 2: chunks outermost
 int g_cta_pairs = 1;              // 0: never; 1: cta_group::2 pairs where they measured faster; 2|3: wherever they are possible
 
 EncodeTiledFn get_encode_tiled() {
@@ -505,6 +530,10 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   constexpr int kFreed = (kRingBytes + C::kStageBytes - 1) / C::kStageBytes;
   a.res_prefetch = (a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && (C::kStages - kFreed >= 2);
   a.nstages = a.res_prefetch ? C::kStages - kFreed : C::kStages;
+  if (a.passes == 3) {                                           // split precision: double-size stages holding the hi and lo tiles
+    if (a.res_prefetch) { set_error_msg("skd_conv2d_fwd_sm100", "split-precision convolution with a residual is not supported"); return 0; }
+    a.nstages = C::kStages / 2;
+  }
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_sm100_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -537,6 +566,7 @@ extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
 extern "C" void skd_set_conv_res_prefetch(int on) { g_res_prefetch = on ? 1 : 0; }
 extern "C" void skd_set_conv_tile_order(int mode) { g_tile_order = mode; g_tile_flip = 0; }
 extern "C" void skd_set_conv_cta_pairs(int mode) { g_cta_pairs = mode & 3; }
+extern "C" void skd_set_conv_k_order(int mode) { g_k_order = mode; }
 
 static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                          const float* x, const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, long long y_row, long long y_img, int oh_req,
@@ -620,6 +650,7 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     a.passes = 3;
   }
   CUtensorMap ty = tx;
+  a.kc_outer = (g_k_order == 2) || (g_k_order == 0 && KH * KW > 1 && Cin >= 2048);
   a.reverse = (g_tile_order == 2) ? (g_tile_flip ^= 1) : g_tile_order;
   a.nstages = 0; a.res_prefetch = 0; a.sumsq = sumsq; a.no_store = no_store;
   a.tma_store = !no_store && (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) && (y_row % 4 == 0) && (y_img % 4 == 0);

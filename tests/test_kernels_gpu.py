@@ -329,6 +329,30 @@ def test_conv_fwd_cta_pairs(ops, case):
         lib().skd_set_conv_cta_pairs(1); lib().skd_set_conv_im2col(1)
 
 
+@pytest.mark.parametrize("case", [(2, 64, 33, 31, 64, 3, 1, 1, 1), (1, 64, 20, 23, 128, 3, 1, 1, 1), (2, 4, 64, 67, 64, 3, 2, 1, 1),
+                                  (1, 128, 17, 19, 256, 3, 1, 2, 2), (3, 64, 9, 13, 32, 1, 1, 0, 1)])
+def test_conv_fwd_split_precision(ops, case):
+    """3xTF32 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo per K step): fp32-grade result, with and without CTA pairs."""
+    from structure_knowledge_distillation_b200._cabi import lib
+    N, Cin, H, W, Cout, k, s, p, d = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    ref = _conv_ref64(x, w, s, p, d) + b.double()[None, :, None, None]
+    xc = ops.to_nhwc(x).contiguous(memory_format=torch.channels_last); wo = ops.weight_ohwi(w)
+    tf32 = rel(ops.conv2d_fwd(xc, wo, s, p, d, shift=b), ref)
+    try:
+        for pairs in (1, 3):
+            lib().skd_set_conv_cta_pairs(pairs)
+            y = ops.conv2d_fwd_3xtf32(xc, wo, s, p, d, shift=b)
+            torch.cuda.synchronize()
+            assert rel(y, ref) < 2e-5, (pairs, rel(y, ref), tf32)      # tensor-core fp32 accumulation truncates: ~1e-5 (one TF32 pass: ~3e-4)
+    finally:
+        lib().skd_set_conv_cta_pairs(1)
+    assert tf32 > 20 * rel(y, ref)                         # the single-pass TF32 result is what the split buys us out of
+
+
 def test_conv_fwd_epilogue_and_pitch(ops):
     """folded-BN scale/shift + residual + ReLU, reading a channel slice and writing into a slice of a wider buffer."""
     g = torch.Generator(device="cuda").manual_seed(7)
