@@ -611,8 +611,11 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   a.n_tiles = (Cout + bn - 1) / bn;
   // CTA pairs (measured, tools/pair_bench.py): +5-11% on the 256-wide non-residual tiles; with a fused residual only when the K loop
   // is long enough (>= 16 chunks) that the two A/B stages the residual ring leaves a single CTA become the limiter
-  const bool pair_ok = bn >= 128 && a.m_tiles >= 2;
-  const bool pair = pair_ok && ((g_cta_pairs & 2) ? true : (g_cta_pairs & 1) ? (bn == 256 && (!residual || Cin * KH * KW >= 512)) : false);
+  // 64-wide tiles: a single CTA's MMAs read 4 KB of A per 2 KB of B from shared memory (operand-read bound at ~1/3 of the tensor
+  // rate); a pair reads 4 KB + 1 KB for twice the work
+  const bool pair_ok = bn >= 64 && a.m_tiles >= 2;
+  const bool auto_pair = (bn == 256 && (!residual || Cin * KH * KW >= 512)) || (bn == 64 && !residual && a.m_tiles >= 4 * kNumSMs);
+  const bool pair = pair_ok && ((g_cta_pairs & 2) ? true : (g_cta_pairs & 1) ? auto_pair : false);
 
   CUtensorMap tx, tw, tx2, tw2;
   auto encode_x = [&](CUtensorMap* m, const float* ptr) -> bool {
@@ -671,7 +674,11 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode(&tr, 4, residual, dims, strides, box, estr, who, true)) return 0;      // plain FLOAT32: the residual is not rounded
   }
-  if (pair) return bn == 256 ? launch<256, 2>(tx, tw, ty, tx2, tw2, tr, a, st) : launch<128, 2>(tx, tw, ty, tx2, tw2, tr, a, st);
+  if (pair) {
+    if (bn == 256) return launch<256, 2>(tx, tw, ty, tx2, tw2, tr, a, st);
+    if (bn == 128) return launch<128, 2>(tx, tw, ty, tx2, tw2, tr, a, st);
+    return launch<64, 2>(tx, tw, ty, tx2, tw2, tr, a, st);
+  }
   switch (bn) {
     case 256: return launch<256, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
     case 128: return launch<128, 1>(tx, tw, ty, tx2, tw2, tr, a, st);

@@ -297,6 +297,8 @@ PAIR_CASES = [
     (2, 1024, 6, 7, 136, 3, 1, 1, 1, False),       # ragged Cout: the second CTA's weight half is mostly out of range
     (1, 100, 20, 23, 72, 3, 1, 1, 1, True),        # Cout 72 -> BLOCK_N 128, second half holds 8 rows
     (2, 256, 65, 129, 256, 3, 1, 2, 2, False),     # teacher layer3 conv2 shape (2 images)
+    (2, 64, 40, 37, 64, 3, 1, 1, 1, False),        # BLOCK_N 64 pairs (student stem / layer1 class)
+    (1, 128, 40, 37, 48, 3, 1, 1, 1, True),        # BLOCK_N 64 pairs, ragged Cout, residual ring
 ]
 
 

@@ -16,6 +16,11 @@ SHAPES = [  # name, N, Cin, H, W, Cout, k, stride, pad, dil, residual
     ("t.psp bottleneck 3x3 4096->512", 8, 4096, 65, 129, 512, 3, 1, 1, 1, False),
     ("s.layer3 3x3 256->256 d2", 8, 256, 65, 129, 256, 3, 1, 2, 2, False),
     ("s.layer4 3x3 512->512 d4", 8, 512, 65, 129, 512, 3, 1, 4, 4, False),
+    ("s.stem conv2 3x3 64->64 @256x512", 8, 64, 256, 512, 64, 3, 1, 1, 1, False),
+    ("s.stem conv3 3x3 64->128 @256x512", 8, 64, 256, 512, 128, 3, 1, 1, 1, False),
+    ("s.stem dgrad 3x3 128->64 @256x512", 8, 128, 256, 512, 64, 3, 1, 1, 1, False),
+    ("s.layer1 3x3 64->64 @129x257", 8, 64, 129, 257, 64, 3, 1, 1, 1, False),
+    ("s.layer2 3x3 128->128 @65x129", 8, 128, 65, 129, 128, 3, 1, 1, 1, False),
 ]
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 def timeit(fn, reps=10):
@@ -23,7 +28,9 @@ def timeit(fn, reps=10):
     for _ in range(reps): fn()
     e.record(); torch.cuda.synchronize(); return s.elapsed_time(e) / reps
 g = torch.Generator(device="cuda").manual_seed(0)
+only = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, N, Cin, H, W, Cout, k, st, p, d, with_res in SHAPES:
+    if not name.startswith(only): continue
     x = ops.to_nhwc(torch.randn(N, Cin, H, W, device="cuda", generator=g))
     w = ops.weight_ohwi(torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5)
     OH = (H + 2 * p - d * (k - 1) - 1) // st + 1; OW = (W + 2 * p - d * (k - 1) - 1) // st + 1
@@ -37,6 +44,11 @@ for name, N, Cin, H, W, Cout, k, st, p, d, with_res in SHAPES:
         t = timeit(lambda: ops.conv2d_fwd(x, w, st, p, d, scale=sc, shift=sh, residual=res, act="relu", out=out))
         ys.append(out.clone())
         cols.append("%s%s %.3f ms %5.1f TF" % ("pair" if pairs else "single", "" if ring else "/noring", t, fl / t / 1e9))
+    if name.startswith("s.stem") or name.startswith("s.layer1"):       # split-precision forward of the same shape
+        for pairs in (0, 3):
+            L.skd_set_conv_cta_pairs(pairs)
+            t = timeit(lambda: ops.conv2d_fwd_3xtf32(x, w, st, p, d))
+            cols.append("3x %s %.3f ms %5.1f TF" % ("pair" if pairs else "single", t, 3 * fl / t / 1e9))
     L.skd_set_conv_cta_pairs(1); L.skd_set_conv_res_prefetch(1)
     diff = max((ys[0] - y).abs().max().item() for y in ys[1:])
     print("%-34s %s | max diff %.2g" % (name, " | ".join(cols), diff), flush=True)
