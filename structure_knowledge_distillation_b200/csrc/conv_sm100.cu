@@ -611,10 +611,11 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   a.n_tiles = (Cout + bn - 1) / bn;
   // CTA pairs (measured, tools/pair_bench.py): +5-11% on the 256-wide non-residual tiles; with a fused residual only when the K loop
   // is long enough (>= 16 chunks) that the two A/B stages the residual ring leaves a single CTA become the limiter
-  // 64-wide tiles: a single CTA's MMAs read 4 KB of A per 2 KB of B from shared memory (operand-read bound at ~1/3 of the tensor
-  // rate); a pair reads 4 KB + 1 KB for twice the work
+  // (64- and 128-wide pair tiles exist for completeness / tests: the student's Cin = 64 convolutions measured identical either way --
+  //  they are bound by the 9x re-read of the activations through L2, ~6.5 TB/s aggregate; DESIGN.md "what limits what")
   const bool pair_ok = bn >= 64 && a.m_tiles >= 2;
-  const bool auto_pair = (bn == 256 && (!residual || Cin * KH * KW >= 512)) || (bn == 64 && !residual && a.m_tiles >= 4 * kNumSMs);
+  const bool kc_outer = (g_k_order == 2) || (g_k_order == 0 && KH * KW > 1 && Cin >= 2048);
+  const bool auto_pair = bn == 256 && !kc_outer && (!residual || Cin * KH * KW >= 512);
   const bool pair = pair_ok && ((g_cta_pairs & 2) ? true : (g_cta_pairs & 1) ? auto_pair : false);
 
   CUtensorMap tx, tw, tx2, tw2;
@@ -653,7 +654,7 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     a.passes = 3;
   }
   CUtensorMap ty = tx;
-  a.kc_outer = (g_k_order == 2) || (g_k_order == 0 && KH * KW > 1 && Cin >= 2048);
+  a.kc_outer = kc_outer;
   a.reverse = (g_tile_order == 2) ? (g_tile_flip ^= 1) : g_tile_order;
   a.nstages = 0; a.res_prefetch = 0; a.sumsq = sumsq; a.no_store = no_store;
   a.tma_store = !no_store && (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) && (y_row % 4 == 0) && (y_img % 4 == 0);

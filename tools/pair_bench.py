@@ -29,6 +29,7 @@ def timeit(fn, reps=10):
     e.record(); torch.cuda.synchronize(); return s.elapsed_time(e) / reps
 g = torch.Generator(device="cuda").manual_seed(0)
 only = sys.argv[1] if len(sys.argv) > 1 else ""
+if len(sys.argv) > 2: L.skd_set_conv_im2col(int(sys.argv[2])); print("im2col mode", sys.argv[2])
 for name, N, Cin, H, W, Cout, k, st, p, d, with_res in SHAPES:
     if not name.startswith(only): continue
     x = ops.to_nhwc(torch.randn(N, Cin, H, W, device="cuda", generator=g))
