@@ -7,19 +7,23 @@
 // Layout: activations NHWC fp32 (row pitch ld*, so channel slices of a concat buffer are addressable in place),
 // weights [Cout][KH][KW][Cin] (K-major), fp32 storage, TF32 tensor-core math with fp32 accumulation in TMEM.
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 0   TMA producer  : per (tap, 32-channel chunk) one 4-D box {32ch, BW, BH, 1} of X (the tile is a BH x BW
-//                            rectangle of output pixels; the tap shift / padding / stride live in the box coordinates,
-//                            out-of-bounds = hardware zero fill) + one 3-D box {32ch, 1 tap, BLOCK_N} of W, both
-//                            128B-swizzled, landing on a full[] mbarrier of a 4..8-stage ring.
-//   warp 1   MMA issuer    : 4 x tcgen05.mma.kind::tf32 (M=128, N=BLOCK_N, K=8) per stage, accumulator in TMEM
-//                            (2 accumulator stages x BLOCK_N columns), tcgen05.commit releases smem stages / signals
-//                            the epilogue.
+// One persistent CTA per SM (or one CTA PAIR per TPC, template parameter PAIR = 2), 10 warps:
+//   warp 0   TMA producer  : per (tap, 32-channel chunk) one A box of X -- 128 consecutive output pixels in TMA im2col mode
+//                            (tap shift / padding / stride / dilation in the tensor map, out-of-bounds = hardware zero fill),
+//                            a flat [pixels][C] box for 1x1 convs, or a BH x BW rectangle in tiled mode -- plus one 3-D box
+//                            {32ch, 1 tap, BLOCK_N} of W, both 128B-swizzled, landing on a full[] mbarrier of a 2..8-stage
+//                            ring.  Split precision (3xTF32): the stage also holds the low parts of both operands.
+//   warp 1   MMA issuer    : 4 x tcgen05.mma.kind::tf32 (M=128, N=BLOCK_N, K=8) per stage (x3 for split precision),
+//                            accumulator in TMEM (2 accumulator stages x BLOCK_N columns), tcgen05.commit releases smem
+//                            stages / signals the epilogue.
 //   warps 2-9 epilogue     : two groups of four warps (one per TMEM lane quarter) take alternate 32-column chunks:
 //                            tcgen05.ld 32x32b -> registers -> fused per-channel scale/shift (folded BN or bias, staged
-//                            in smem), residual add, ReLU / leaky-ReLU -> 128B-swizzled smem staging -> TMA store of the
-//                            BH x BW x 32ch box (coalesced, async, hardware-clipped at the ragged edges).
-//                            Overlaps the next tile's MMAs through the second TMEM accumulator stage.
+//                            in smem), residual add (residual boxes arrive through a per-group TMA ring), ReLU /
+//                            leaky-ReLU -> 128B-swizzled smem staging -> TMA store of the 128px x 32ch box (coalesced,
+//                            async, hardware-clipped at the ragged edges).  Overlaps the next tile's MMAs through the
+//                            second TMEM accumulator stage.
+//   PAIR = 2               : cluster of two CTAs, tcgen05 cta_group::2: M = 256 per tile, each CTA stages its own 128 pixels
+//                            and half of the weight tile; the leader CTA issues the MMAs and multicasts the commits.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -648,7 +652,7 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   };
   if (!encode_x(&tx, x) || !encode_w(&tw, w)) return 0;
   tx2 = tx; tw2 = tw; a.passes = 1;
-  if (x_lo && w_lo) {                                          // split-precision operands: three accumulation passes
+  if (x_lo && w_lo) {                                          // split-precision operands: three MMAs per K step
     if ((reinterpret_cast<uintptr_t>(x_lo) | reinterpret_cast<uintptr_t>(w_lo)) & 15) { set_error_msg(who, "x_lo / w_lo not 16-byte aligned"); return 0; }
     if (!encode_x(&tx2, x_lo) || !encode_w(&tw2, w_lo)) return 0;
     a.passes = 3;
