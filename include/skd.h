@@ -125,6 +125,12 @@ int skd_conv2d_fwd_sm100_3xtf32(int N, int H, int W, int Cin, int Cout, int KH, 
                                 const float* x_lo, int ldx, const float* w_hi, const float* w_lo, float* y, int ldy, const float* scale,
                                 const float* shift, int act, float slope, cudaStream_t);
 int skd_split_tf32(long long n, const float* src, float* hi, float* lo, cudaStream_t);
+/* general form of the tcgen05 forward (discriminator path): optional split-precision operands (x_lo / w_lo both NULL -> plain TF32),
+   optional output extent (out_h / out_w > 0: positions past the natural size read zero-filled input), fused scale / shift / residual / act */
+int skd_conv2d_fwd_sm100_ex(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                            const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, int out_h, int out_w,
+                            const float* scale, const float* shift, const float* residual, int ldr, int act, float slope, cudaStream_t);
+
 /* same kernel, output written through explicit element strides y[n*y_img + oy*y_row + ox*y_pix + c] (every-other-pixel sub-grids:
    the data gradient of a stride-2 convolution is 4 stride-1 convolutions of dy, one per input-pixel parity class) */
 int skd_conv2d_fwd_sm100_strided(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
@@ -176,6 +182,76 @@ int skd_slice_copy(long long rows, int C, const float* src, int src_pitch, int s
 /* G_solver.step (networks/kd_model.py:74,171): v = mu*v + (g*grad_scale + wd*p); p -= lr*v; lr read from device memory */
 int skd_sgd_step(long long n, float* param, const float* grad, float* momentum_buf, const float* lr, float momentum,
                  float weight_decay, int first_step, float grad_scale, cudaStream_t);
+
+
+/* ---- F. SAGAN discriminator of the holistic loss (networks/sagan_models.py:9-41,105-168, networks/spectral.py:23-35) and the
+        adversarial criteria (utils/criterion.py:92-166).  Activations are NHWC rows [positions][channels].  "+=" outputs honour
+        `accumulate` (the reference's native convention: caller-zeroed dweight/dbias, libs/src/bn.cu:214-230). ---- */
+/* SpectralNorm._update_u_v (spectral.py:23-35), ONE power iteration: v <- normalize(W^T u), u <- normalize(W v), sigma = u.(W v).
+   w_bar is [Cout][taps][Cin] (OHWI storage of the (Cout,Cin,KH,KW) parameter); v keeps the reference's flattening (ci*taps + tap).
+   u, v advance in place; u_save / v_save (may be NULL) receive copies for the backward; inv_sigma_vec[vec_len] is filled with
+   1/sigma (per-channel epilogue scale of the convolution: conv(x, w_bar/sigma) = conv(x, w_bar)/sigma).  One cluster of 8 CTAs. */
+int skd_sn_power_iter(int Cout, int taps, int Cin, const float* w_bar, float* u, float* v, float* u_save, float* v_save, float* sigma,
+                      float* inv_sigma_vec, int vec_len, cudaStream_t);
+/* d_w (+)= d_wn/sigma - <d_wn, w_bar>/sigma^2 * u v^T : gradient through w_bar/sigma with u, v constant (spectral.py:34-35).
+   d_wn is [Cout][taps][Cin_p] (channel-padded wgrad output), d_w / w_bar [Cout][taps][Cin]. */
+long long skd_sn_weight_grad_workspace_doubles(void);      /* zero-initialised once by the caller; self-resetting */
+int skd_sn_weight_grad(int Cout, int taps, int Cin, int Cin_p, const float* d_wn, const float* w_bar, const float* u, const float* v,
+                       const float* sigma, float* d_w, int accumulate, double* workspace, cudaStream_t);
+/* w [rows][Cin] -> channel-padded copy [rows][Cin_p] (+ its TF32 "lo" part, may be NULL) */
+int skd_disc_weight_prep(long long rows, int Cin, int Cin_p, const float* w, float* w_pad, float* w_lo, cudaStream_t);
+/* data-gradient weights of a 4x4 / stride 2 / pad 1 convolution as ONE 3x3 stride-1 convolution of dy whose 4*Cin_p output channels
+   are the four input-pixel parity classes: wd[(py*2+px)*Cin_p+ci][3][3][Cout] */
+int skd_disc_dgrad_weight_prep(int Cout, int Cin, int Cin_p, const float* w, float* wd, float* wd_lo, cudaStream_t);
+/* un-shuffle that convolution's output d2s [B][ceil(H/2)][ceil(W/2)][4*Cp] into dx [B][H][W][Cq] (channels >= C zero), multiplied by
+   the LeakyReLU mask recovered from ref [ref_batch][H][W][C] (post-activation output of the layer below; NULL: no mask) */
+int skd_disc_dgrad_unshuffle(int B, int H, int W, int C, int Cp, const float* d2s, const float* ref, int ref_batch, float slope, float* out,
+                             int Cq, float* out_lo, cudaStream_t);
+/* out = in * leaky'(ref[i % period]) (+ TF32 lo part) */
+int skd_disc_mask_mul(long long n, long long period, const float* ref, const float* in, float* out, float* out_lo, float slope, cudaStream_t);
+/* nn.BatchNorm2d(C <= 32) with batch statistics (sagan_models.py:147): x addressed by (sn, sc, sp) strides */
+long long skd_bn2d_workspace_doubles(void);                /* zero-initialised once by the caller; self-resetting */
+int skd_bn2d_stats(int N, int C, int HW, const float* x, long long sn, long long sc, long long sp, float eps, float momentum,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, float* mean, float* rstd, double* workspace,
+                   cudaStream_t);
+int skd_bn2d_apply(int N, int C, int HW, const float* x, long long sn, long long sc, long long sp, const float* mean, const float* rstd,
+                   const float* weight, const float* bias, float* out, float* out_lo, int Cp, cudaStream_t);
+/* sums[0..31] = sum a, sums[32..63] = sum a*xhat, sums[64..95] = sum a*b (b may be NULL); a, b dense [N*HW][ld] */
+int skd_bn2d_reduce(int N, int C, int HW, const float* x, long long sn, long long sc, long long sp, const float* mean, const float* rstd,
+                    const float* a, const float* b, int ld, float* sums, double* workspace, cudaStream_t);
+/* out = gamma rstd (a - mean(a) - xhat mean(a xhat)): BN's input gradient and (symmetric Jacobian) its forward-mode tangent */
+int skd_bn2d_jacobian(int N, int C, int HW, const float* x, long long sn, long long sc, long long sp, const float* mean, const float* rstd,
+                      const float* weight, const float* a, int ld, const float* sums, float* out, long long on, long long oc, long long op,
+                      int Cq, float* out_lo, cudaStream_t);
+/* dgamma (+)= sum gh xhat [+ sum gth t0], dbeta (+)= sum gh; sums_t / sums_v NULL for the first-order backward */
+int skd_bn2d_param_grad(int C, long long P, const float* rstd, const float* sums_g, const float* sums_t, const float* sums_v, float* dgamma,
+                        float* dbeta, int accumulate, cudaStream_t);
+/* Self_Attn core (sagan_models.py:31-40): A = softmax(Q K^T) (no 1/sqrt(d)), O = A V, y = gamma O + x.
+   qkv [B*n][ldq] = [q(d) | k(d) | v(C)] (the three 1x1 convolutions as one GEMM), x / o / y [B*n][C], attn [B][n][n]; n <= 128, d <= 64 */
+int skd_attn_fwd(int B, int n, int C, int d, const float* qkv, int ldq, const float* x, const float* gamma, float* attn, float* o, float* y,
+                 float* y_lo, cudaStream_t);
+/* forward-mode tangent along (tqkv, tx): dattn = Adot, to = Odot, ty = gamma Odot + tx */
+int skd_attn_tangent_fwd(int B, int n, int C, int d, const float* qkv, const float* tqkv, int ldq, const float* attn, const float* tx,
+                         const float* gamma, float* dattn, float* to, float* ty, float* ty_lo, cudaStream_t);
+/* backward: gy = adjoint of y (NULL: zero).  gty != NULL selects the JOINT backward of (y, ydot) used by the WGAN-GP penalty
+   (oracle/gp_dual.py attn_joint_backward); gqkv / gtqkv receive the adjoints of qkv / tqkv, ggamma (+)= dgamma */
+long long skd_attn_bwd_workspace_floats(int B, int n, int C);
+int skd_attn_bwd(int B, int n, int C, int d, const float* qkv, int ldq, const float* attn, const float* o, const float* gamma,
+                 const float* gy, const float* tqkv, const float* dattn, const float* to, const float* gty, float* gqkv, float* gtqkv,
+                 float* ggamma, int accumulate, float* workspace, cudaStream_t);
+/* the "last" convolution (sagan_models.py:140: Conv2d(C, 1, 4), no padding): w [KH][KW][C] with row pitch w_row floats */
+int skd_disc_last_fwd(int B, int H, int W, int C, int KH, int KW, const float* x, const float* w, int w_row, const float* bias, float* out,
+                      cudaStream_t);
+int skd_disc_last_dgrad(int B, int H, int W, int C, int KH, int KW, const float* gout, const float* w, int w_row, float* gx, float* gx_lo,
+                        cudaStream_t);                       /* gout NULL: all ones */
+int skd_disc_last_wgrad(int B, int H, int W, int C, int KH, int KW, const float* x, const float* gout, float* gw, int w_row, float* gbias,
+                        int accumulate, cudaStream_t);
+/* CriterionAdv / CriterionAdvForG (utils/criterion.py:129-166): type 0 wgan-gp, 1 hinge, 2 generator; also d loss / d out */
+int skd_adv_loss(int n, const float* real, const float* fake, int type, float* loss, float* g_real, float* g_fake, cudaStream_t);
+/* CriterionAdditionalGP (utils/criterion.py:98-120): norms[b] = |g_b|, loss = lambda * mean (|g_b| - 1)^2 */
+int skd_gp_norms(int B, long long len, const float* g, float lambda_gp, float* norms, float* loss, cudaStream_t);
+/* v_b = upstream * 2 lambda / B * (|g_b| - 1) / |g_b| * g_b  (upstream: device scalar or NULL) */
+int skd_gp_direction(int B, long long len, const float* g, const float* norms, float lambda_gp, const float* upstream, float* v, cudaStream_t);
 
 #ifdef __cplusplus
 }

@@ -532,12 +532,10 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   // residual epilogues are HBM-bound: trade A/B pipeline depth for the residual TMA ring (2 groups x kResSlots x 16 KB)
   constexpr int kRingBytes = 2 * kResSlots * C::kOutStageBytes;
   constexpr int kFreed = (kRingBytes + C::kStageBytes - 1) / C::kStageBytes;
-  a.res_prefetch = (a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && (C::kStages - kFreed >= 2);
+  // (split precision keeps every stage for its double-size {hi, lo} tiles: a fused residual is then read coalesced by the epilogue warps)
+  a.res_prefetch = (a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && (C::kStages - kFreed >= 2) && a.passes != 3;
   a.nstages = a.res_prefetch ? C::kStages - kFreed : C::kStages;
-  if (a.passes == 3) {                                           // split precision: double-size stages holding the hi and lo tiles
-    if (a.res_prefetch) { set_error_msg("skd_conv2d_fwd_sm100", "split-precision convolution with a residual is not supported"); return 0; }
-    a.nstages = C::kStages / 2;
-  }
+  if (a.passes == 3) a.nstages = C::kStages / 2;                 // split precision: double-size stages holding the hi and lo tiles
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_sm100_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -597,8 +595,12 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   const bool strided_out = (y_row != (long long)OW * ldy) || (y_img != (long long)OH * y_row);
   const bool flat = !strided_out && (KH == 1 && KW == 1 && stride == 1 && pad == 0);
   const long long P = (long long)N * OH * OW;
-  const int up_h = pad - (KH - 1) * dil, up_w = pad - (KW - 1) * dil;
-  const bool can_im2col = !flat && !strided_out && g_conv_im2col && get_encode_im2col() && pad <= 128 && up_h >= -128 && up_w >= -128 && stride <= 8 &&
+  // TMA im2col bounding box: the last filter origin is dim - 1 + upper.  A caller-chosen extent moves it so that exactly OH x OW
+  // origins exist (rows / columns past the input read hardware zero fill)
+  const int up_h = oh_req > 0 ? (OH - 1) * stride - pad - (H - 1) : pad - (KH - 1) * dil;
+  const int up_w = ow_req > 0 ? (OW - 1) * stride - pad - (W - 1) : pad - (KW - 1) * dil;
+  const bool can_im2col = !flat && !strided_out && g_conv_im2col && get_encode_im2col() && pad <= 128 && up_h >= -128 && up_w >= -128 && up_h <= 127 &&
+                          up_w <= 127 && stride <= 8 &&
                           P < (1LL << 31) && (KH - 1) * dil < 65536;
   int vN = N, vH = H, vW = W;                                // geometry of the tiled-mode input view
   if (flat) { vN = 1; vH = 1; vW = (int)P; a.N = 1; a.OH = 1; a.OW = (int)P; a.BH = 1; a.BW = 128; }
@@ -726,4 +728,18 @@ extern "C" int skd_conv2d_fwd_sm100_3xtf32(int N, int H, int W, int Cin, int Cou
   const int OH = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, OW = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
   return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x_hi, x_lo, ldx, w_hi, w_lo, y, ldy, (long long)OW * ldy,
                        (long long)OH * OW * ldy, 0, 0, nullptr, 0, scale, shift, nullptr, 0, act, slope, 0, st);
+}
+
+// General entry (discriminator path, networks/sagan_models.py): optional split-precision operands (x_lo / w_lo NULL -> plain TF32),
+// optional output extent (out_h / out_w > 0: rows / columns past the natural size see zero-filled input), fused per-channel
+// scale / shift, residual add and activation.
+extern "C" int skd_conv2d_fwd_sm100_ex(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                                       const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, int out_h, int out_w,
+                                       const float* scale, const float* shift, const float* residual, int ldr, int act, float slope,
+                                       cudaStream_t st) {
+  const int OH = out_h > 0 ? out_h : (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+  const int OW = out_w > 0 ? out_w : (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+  if ((x_lo == nullptr) != (w_lo == nullptr)) { set_error_msg("skd_conv2d_fwd_sm100_ex", "x_lo and w_lo must be given together"); return 0; }
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, x_lo, ldx, w, w_lo, y, ldy, (long long)OW * ldy, (long long)OH * OW * ldy,
+                       out_h, out_w, nullptr, 0, scale, shift, residual, ldr, act, slope, 0, st);
 }

@@ -76,9 +76,8 @@ class NetModel():
             p.requires_grad_(False)
         self.parallel_teacher = self.teacher
 
-        # The discriminator (0.03 % of the FLOPs) still runs on torch's differentiable operators (double backward for the
-        # WGAN-GP penalty) with torch's defaults (cuDNN convolutions in TF32; forcing fp32 there costs 5 ms/step and does not
-        # move the D-loss parity, which is governed by the student-logit precision)
+        # SAGAN discriminator on the sm_100a kernels (networks/sagan_engine.py): tcgen05 spectral-norm convolutions, fused
+        # attention, and the WGAN-GP penalty by a tangent + joint reverse pass instead of autograd's double backward
         D_model = Discriminator(args.preprocess_GAN_mode, args.classes_num, args.batch_size, args.imsize_for_adv, args.adv_conv_dim)
         self.D_model = D_model.float().to(device).train()
         self.parallel_D = self.D_model
@@ -177,19 +176,18 @@ class NetModel():
         if args.ho == True:
             d_out_S = self.parallel_D(self.preds_S[0])
             G_loss = G_loss + args.lambda_d * self.criterion_adv_for_G(d_out_S, d_out_S)
-        G_loss.backward()
+        # the generator step only needs d D(S) / d logits: the reference's D gradients of this pass are discarded by
+        # D_solver.zero_grad() (kd_model.py:154), so they are not computed
+        self.D_model.skip_param_grads = True
+        try:
+            G_loss.backward()
+        finally:
+            self.D_model.skip_param_grads = False
+            self.D_model.engine.release()
         self.G_loss = _LazyScalar(G_loss)
 
     def discriminator_backward(self):
-        self.D_solver.zero_grad()
-        args = self.args
-        d_out_T = self.parallel_D(self.preds_T[0].detach())
-        d_out_S = self.parallel_D(self.preds_S[0].detach())
-        d_loss = args.lambda_d * self.criterion_adv(d_out_S, d_out_T)
-        if args.adv_loss_type == 'wgan-gp':
-            d_loss = d_loss + args.lambda_d * self.criterion_AdditionalGP(self.preds_S, self.preds_T)
-        d_loss.backward()
-        self.D_loss = _LazyScalar(d_loss)
+        self._discriminator_phase()
         self.D_solver.all_reduce_grads(self.world)
         self.D_solver.step()
 
@@ -202,12 +200,19 @@ class NetModel():
         """discriminator_backward() without the optimizer step (kd_model.py:153-163)."""
         self.D_solver.zero_grad()
         args = self.args
-        d_out_T = self.parallel_D(self.preds_T[0].detach())
-        d_out_S = self.parallel_D(self.preds_S[0].detach())
-        d_loss = args.lambda_d * self.criterion_adv(d_out_S, d_out_T)
-        if args.adv_loss_type == 'wgan-gp':
-            d_loss = d_loss + args.lambda_d * self.criterion_AdditionalGP(self.preds_S, self.preds_T)
-        d_loss.backward()
+        D = self.D_model
+        D.engine.prepare()                                   # weights are constant within the phase: stage them once
+        D.accumulate_into_grad = True                        # the three passes add straight into FlatSGD's gradient buffer
+        try:
+            d_out_T = self.parallel_D(self.preds_T[0].detach())
+            d_out_S = self.parallel_D(self.preds_S[0].detach())
+            d_loss = args.lambda_d * self.criterion_adv(d_out_S, d_out_T)
+            if args.adv_loss_type == 'wgan-gp':
+                d_loss = d_loss + args.lambda_d * self.criterion_AdditionalGP(self.preds_S, self.preds_T)
+            d_loss.backward()
+        finally:
+            D.accumulate_into_grad = False
+            D.engine.release()
         self.D_loss = _LazyScalar(d_loss)
 
     def optimize_parameters(self):

@@ -1,5 +1,6 @@
-"""Spectral normalisation wrapper with the reference's state-dict layout (networks/spectral.py): the wrapped module
-keeps `<name>_bar`, `<name>_u`, `<name>_v`; one power iteration per forward; sigma differentiates w.r.t. w_bar only."""
+"""Spectral normalisation wrapper with the reference's state-dict layout (networks/spectral.py): the wrapped module keeps
+`<name>_bar`, `<name>_u`, `<name>_v`; one power iteration per forward (csrc/disc.cu: sn_power_iter_kernel, one 8-CTA
+cluster combining W^T u through distributed shared memory); sigma differentiates w.r.t. w_bar only (u, v are `.data`)."""
 import torch
 from torch import nn
 from torch.nn import Parameter
@@ -13,33 +14,22 @@ class SpectralNorm(nn.Module):
     def __init__(self, module, name='weight', power_iterations=1):
         super().__init__()
         self.module, self.name, self.power_iterations = module, name, power_iterations
+        if power_iterations != 1:
+            raise ValueError("one power iteration per forward (the only setting the reference uses, sagan_models.py:117-133)")
         if not hasattr(module, name + "_u"):
             w = getattr(module, name)
             height = w.shape[0]
-            width = w.view(height, -1).shape[1]
+            width = w.numel() // height
             u = Parameter(l2normalize(w.data.new(height).normal_(0, 1)), requires_grad=False)
             v = Parameter(l2normalize(w.data.new(width).normal_(0, 1)), requires_grad=False)
-            w_bar = Parameter(w.data)
+            w_bar = Parameter(w.data)                      # keeps the channels-last (OHWI) storage of the wrapped conv
             del module._parameters[name]
             module.register_parameter(name + "_u", u)
             module.register_parameter(name + "_v", v)
             module.register_parameter(name + "_bar", w_bar)
 
-    def _update_u_v(self):
-        m, n = self.module, self.name
-        u, v, w = getattr(m, n + "_u"), getattr(m, n + "_v"), getattr(m, n + "_bar")
-        w2 = w.view(w.shape[0], -1)
-        with torch.no_grad():
-            nu, nv = u, v
-            for _ in range(self.power_iterations):
-                nv = l2normalize(torch.mv(w2.t(), nu))
-                nu = l2normalize(torch.mv(w2, nv))
-            # persistent state advances in place (CUDA-graph safe); autograd saves the fresh nu/nv, so several forwards
-            # before one backward (kd_model.py:156-161) do not trip the version counter
-            v.copy_(nv); u.copy_(nu)
-        sigma = nu.dot(w2.mv(nv))
-        setattr(m, n, w / sigma.expand_as(w))
-
-    def forward(self, *args):
-        self._update_u_v()
-        return self.module.forward(*args)
+    def forward(self, x):
+        """Stand-alone use: y = conv(x, w_bar / sigma) + bias after one power iteration."""
+        from .sagan_engine import SNConvFn
+        m = self.module
+        return SNConvFn.apply(m, x, m.weight_bar, m.bias)

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import functions as Fn
+from ..networks.sagan_engine import AdvLossFn, GradientPenaltyFn
 
 
 class CriterionPixelWise(nn.Module):
@@ -63,7 +64,8 @@ class CriterionAdvForG(nn.Module):
         self.adv_loss = adv_type
 
     def forward(self, d_out_S, d_out_S_no_use=None):
-        return -d_out_S[0].mean()
+        """-mean(D(S)) for both adversarial types (criterion.py:129-137)."""
+        return AdvLossFn.apply(None, d_out_S[0], 2)
 
 
 class CriterionAdv(nn.Module):
@@ -75,13 +77,15 @@ class CriterionAdv(nn.Module):
 
     def forward(self, d_out_S, d_out_T):
         assert d_out_S[0].shape == d_out_T[0].shape, 'the output dim of D with teacher and student as input differ'
-        real, fake = d_out_T[0], d_out_S[0]
-        if self.adv_loss == 'wgan-gp':
-            return -real.mean() + fake.mean()
-        return torch.relu(1.0 - real).mean() + torch.relu(1.0 + fake).mean()
+        return AdvLossFn.apply(d_out_T[0], d_out_S[0], 0 if self.adv_loss == 'wgan-gp' else 1)
 
 
 class CriterionAdditionalGP(nn.Module):
+    """WGAN-GP penalty lambda * mean((|d D(x)/dx|_2 - 1)^2) at x = alpha real + (1 - alpha) fake (criterion.py:98-120).
+    The reference differentiates it by double backward through D; here the value and the parameter gradient come from the
+    discriminator engine's first-order chain / tangent pass / joint reverse pass (networks/sagan_engine.py) -- `D_net` must be
+    this package's Discriminator."""
+
     def __init__(self, D_net, lambda_gp):
         super().__init__()
         self.D = D_net
@@ -90,10 +94,10 @@ class CriterionAdditionalGP(nn.Module):
 
     def forward(self, d_in_S, d_in_T):
         assert d_in_S[0].shape == d_in_T[0].shape, 'the output dim of D with teacher and student as input differ'
+        D = self.D
+        if not hasattr(D, "engine"):
+            raise TypeError("CriterionAdditionalGP needs structure_knowledge_distillation_b200's Discriminator (no autograd double backward here)")
         real, fake = d_in_T[0].detach(), d_in_S[0].detach()
         alpha = self.alpha if self.alpha is not None else torch.rand(real.size(0), 1, 1, 1, device=real.device)
-        x = (alpha * real + (1 - alpha) * fake).requires_grad_(True)
-        out = self.D(x)
-        (grad,) = torch.autograd.grad(out[0], x, torch.ones_like(out[0]), retain_graph=True, create_graph=True)
-        norm = grad.reshape(grad.size(0), -1).pow(2).sum(1).sqrt()
-        return self.lambda_gp * ((norm - 1) ** 2).mean()
+        x = torch.lerp(fake, real, alpha.to(real.dtype))               # alpha * real + (1 - alpha) * fake
+        return GradientPenaltyFn.apply(D, x, float(self.lambda_gp), *[p for p in D.parameters() if p.requires_grad])
