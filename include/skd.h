@@ -253,6 +253,14 @@ int skd_gp_norms(int B, long long len, const float* g, float lambda_gp, float* n
 /* v_b = upstream * 2 lambda / B * (|g_b| - 1) / |g_b| * g_b  (upstream: device scalar or NULL) */
 int skd_gp_direction(int B, long long len, const float* g, const float* norms, float lambda_gp, const float* upstream, float* v, cudaStream_t);
 
+/* ---- G. evaluation (networks/evaluate.py:75-206): full [H][W][C] += bilinear(align_corners) up-sampling of one tile's class scores
+        (C, h, w; strides sc, sp) to tile_h x tile_w, valid part only, placed at (y1, x1); then arg-max + confusion matrix (+=),
+        labels == ignore_index skipped; pred (uint8 [H][W]) optional ---- */
+int skd_eval_upsample_accumulate(int C, int h, int w, const float* logits, long long sc, long long sp, int tile_h, int tile_w, int valid_h,
+                                 int valid_w, float* full, int W, int y1, int x1, cudaStream_t);
+int skd_eval_argmax_confusion(int H, int W, int C, const float* full, const long long* gt, long long gt_row, int valid_h, int valid_w,
+                              int ignore_index, long long* confusion, unsigned char* pred, cudaStream_t);
+
 #ifdef __cplusplus
 }
 #endif

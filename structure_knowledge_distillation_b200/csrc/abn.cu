@@ -345,7 +345,7 @@ __global__ void nhwc_stats_finalize_kernel(const float* __restrict__ x, const fl
   mean[c] = mu; var[c] = v;
   if (running_mean) {                                              // libs/functions.py:90-91
     running_mean[c] = running_mean[c] * (1.f - momentum) + momentum * mu;
-    running_var[c] = running_var[c] * (1.f - momentum) + momentum * v * count / (count - 1.f);
+    running_var[c] = running_var[c] * (1.f - momentum) + momentum * v * (count > 1.f ? count / (count - 1.f) : 1.f);   // n/(n-1) (functions.py:91); a single sample keeps the biased value instead of 0 * inf
   }
   const float invstd = 1.f / sqrtf(v + eps);
   const float gamma = weight ? fabsf(weight[c]) + eps : 1.f;

@@ -193,9 +193,10 @@ class ABN(torch.autograd.Function):
     def backward(ctx, dout):
         x, out, st, weight, chan_mul = ctx.saved_tensors
         training, eps, activation, slope, has_res = ctx.cfg
-        if not training:
-            raise NotImplementedError("eval-mode ABN backward is not on the distillation path (teacher runs under no_grad)")
-        dx, dres, dw, db = ops.abn_backward(x, out, ops.to_nhwc(dout), st, weight, eps, activation, slope, chan_mul, has_res)
+        # eval mode (libs/functions.py:144-147): edz = eydz = 0 -> dx = dz * gamma * rsqrt(var + eps), and -- a quirk of the
+        # reference kept as is -- dweight = sign(w) * eydz * n = 0, dbias = edz * n = 0
+        dx, dres, dw, db = ops.abn_backward(x, out, ops.to_nhwc(dout), st, weight, eps, activation, slope, chan_mul, has_res,
+                                            training=training)
         return dx, dw, db, None, None, None, None, None, None, None, dres, None
 
 

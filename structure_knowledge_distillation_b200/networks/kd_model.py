@@ -25,6 +25,8 @@ from .. import ops
 from ..optim import FlatSGD
 from ..utils.criterion import (CriterionAdditionalGP, CriterionAdv, CriterionAdvForG, CriterionDSN,
                                CriterionPairWiseforWholeFeatAfterPool, CriterionPixelWise)
+from ..utils.utils import load_D_model, load_S_model, load_T_model
+from .evaluate import evaluate_main
 from .pspnet_combine import BasicBlock, Bottleneck, Res_pspnet
 from .sagan_models import Discriminator
 
@@ -65,12 +67,12 @@ class NetModel():
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
         student = Res_pspnet(BasicBlock, [2, 2, 2, 2], num_classes=args.classes_num)
-        self._load(student, _arg(args, "S_ckpt_path", None), _arg(args, "student_pretrain_model_imgnet", None))
+        load_S_model(args, student, False)                         # ImageNet init or S_resume (utils/utils.py:93-127)
         self.student = student.float().to(device).train()
         self.parallel_student = self.student
 
         teacher = Res_pspnet(Bottleneck, [3, 4, 23, 3], num_classes=args.classes_num)
-        self._load_teacher(teacher, _arg(args, "T_ckpt_path", None))
+        load_T_model(teacher, _arg(args, "T_ckpt_path", None))
         self.teacher = teacher.float().to(device).eval()
         for p in self.teacher.parameters():
             p.requires_grad_(False)
@@ -79,6 +81,7 @@ class NetModel():
         # SAGAN discriminator on the sm_100a kernels (networks/sagan_engine.py): tcgen05 spectral-norm convolutions, fused
         # attention, and the WGAN-GP penalty by a tangent + joint reverse pass instead of autograd's double backward
         D_model = Discriminator(args.preprocess_GAN_mode, args.classes_num, args.batch_size, args.imsize_for_adv, args.adv_conv_dim)
+        load_D_model(args, D_model, False)
         self.D_model = D_model.float().to(device).train()
         self.parallel_D = self.D_model
 
@@ -87,6 +90,8 @@ class NetModel():
         self.D_solver = FlatSGD([p for p in self.D_model.parameters() if p.requires_grad], args.lr_d, momentum=args.momentum,
                                 weight_decay=args.weight_decay)
         self.best_mean_IU = _arg(args, "best_mean_IU", 0.0)
+        if self.world > 1:
+            self._sync_replicas()
 
         self.criterion = CriterionDSN()
         self.criterion_pixel_wise = CriterionPixelWise()
@@ -108,32 +113,18 @@ class NetModel():
         if snap and not os.path.exists(snap):
             os.makedirs(snap, exist_ok=True)
 
-    # ---- checkpoint helpers (utils/utils.py:73-127 semantics: key remap for the teacher, key intersection for ImageNet)
-    @staticmethod
-    def _load_teacher(model, path):
-        if not path or not os.path.exists(path):
-            logging.info("=> no teacher ckpt find")
-            return
-        saved = torch.load(path, map_location="cpu")
-        new = model.state_dict()
-        for k, v in saved.items():
-            if k.startswith('fc.'):
-                continue
-            if k.startswith('head.0.'):
-                new['pspmodule.' + k[7:]] = v
-            elif k.startswith('head.1.'):
-                new['head.' + k[7:]] = v
-            else:
-                new[k] = v
-        model.load_state_dict(new)
-
-    @staticmethod
-    def _load(model, ckpt_dir, imagenet):
-        if imagenet and os.path.isfile(str(imagenet)):
-            saved = torch.load(imagenet, map_location="cpu")
-            cur = model.state_dict()
-            cur.update({k: v for k, v in saved.items() if k in cur})
-            model.load_state_dict(cur)
+    def _sync_replicas(self):
+        """One process per GPU: every rank starts from rank 0's student / discriminator parameters, BN running statistics and
+        spectral-norm vectors (the reference's single-process nn.DataParallel replicates module 0 every step,
+        utils/parallel.py:102-111; without this, layers that no checkpoint covers would differ per rank)."""
+        dist.broadcast(self.G_solver.flat_p, 0)
+        dist.broadcast(self.D_solver.flat_p, 0)
+        for mod in (self.student, self.D_model):
+            for b in mod.buffers():
+                dist.broadcast(b, 0)
+            for p in mod.parameters():
+                if not p.requires_grad:                             # weight_u / weight_v live outside the flat buffers
+                    dist.broadcast(p.data, 0)
 
     # ---- the reference's step API ------------------------------------------------------------------------
     def set_input(self, data):
@@ -269,7 +260,8 @@ class NetModel():
             self.D_solver.all_reduce_grads(self.world); self.D_solver.step()
 
     def evalute_model(self, model, loader, gpu_id, input_size, num_classes, whole):
-        raise NotImplementedError("evaluation (networks/evaluate.py) is outside the distillation hot path; see DESIGN.md")
+        mean_IU, IU_array = evaluate_main(model=model, loader=loader, gpu_id=gpu_id, input_size=input_size, num_classes=num_classes, whole=whole)
+        return mean_IU, IU_array
 
     def print_info(self, epoch, step):
         logging.info('step:{:5d} G_lr:{:.6f} G_loss:{:.5f}(mc:{:.5f} pixelwise:{:.5f} pairwise:{:.5f}) D_lr:{:.6f} D_loss:{:.5f}'.format(
@@ -277,4 +269,6 @@ class NetModel():
             float(self.pa_G_loss), self.D_solver.param_groups[-1]['lr'], float(self.D_loss)))
 
     def save_ckpt(self, epoch, step, mean_IU, IU_array):
+        if self.world > 1 and dist.get_rank() != 0:
+            return                                                  # replicas are identical: rank 0 writes
         torch.save(self.student.state_dict(), osp.join(self.args.snapshot_dir, 'CS_scenes_' + str(step) + '_' + str(mean_IU) + '.pth'))

@@ -65,7 +65,11 @@ def conv3x3(in_planes, out_planes, stride=1):
 
 def _fold(bn):
     """eval-mode ABN -> per-channel (scale, shift) for a conv epilogue (libs/src/bn.cu:140-165 with running stats).
-    Cached per module; the tensors' version counters invalidate it when a checkpoint is loaded or stats change."""
+    Cached only for FROZEN modules (the teacher: requires_grad False), where a checkpoint load (copy_ bumps the version counters)
+    is the only thing that can change the inputs.  Trainable modules are folded afresh on every eval forward: their statistics
+    and affine parameters are written through raw pointers by the stats / SGD kernels, which no version counter sees."""
+    if bn.weight is not None and bn.weight.requires_grad:
+        return ops.abn_fold(bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.eps)
     key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
            bn.weight.data_ptr(), bn.running_mean.data_ptr())
     cached = getattr(bn, "_folded", None)

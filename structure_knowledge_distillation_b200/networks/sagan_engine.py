@@ -515,6 +515,7 @@ class AdvLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, real, fake, kind):
+        ops._f32(fake, real)
         fake = fake.contiguous()
         real = real.contiguous() if real is not None else None
         loss = torch.empty((), device=fake.device, dtype=torch.float32)

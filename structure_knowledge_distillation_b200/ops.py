@@ -128,7 +128,7 @@ def abn_apply(x, scale, shift, act, slope, residual=None, chan_mul=None, out=Non
     return out
 
 
-def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dres, round_tf32=False):
+def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dres, round_tf32=False, training=True):
     """-> dx, dres (or None), dweight, dbias"""
     n, c, h, w, pitch = nhwc_meta(x)
     if nhwc_meta(out)[4] != c or nhwc_meta(dout)[4] != c or pitch != c:
@@ -138,9 +138,12 @@ def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dr
     dev = x.device
     splits = L.skd_abn_num_splits(P, c)
     ws = torch.empty(splits * c * 2, device=dev)
-    red = torch.empty(4, c, device=dev)              # edz, eydz, dweight, dbias
-    L.skd_abn_bwd_reduce_nhwc(P, c, h * w, _p(x), _p(out), _p(dout), _p(stats[0]), _p(stats[1]), _p(weight), eps, ACT[act],
-                              slope, _p(chan_mul), _p(red[0]), _p(red[1]), _p(red[2]), _p(red[3]), _p(ws), splits, _st())
+    if training:
+        red = torch.empty(4, c, device=dev)          # edz, eydz, dweight, dbias
+        L.skd_abn_bwd_reduce_nhwc(P, c, h * w, _p(x), _p(out), _p(dout), _p(stats[0]), _p(stats[1]), _p(weight), eps, ACT[act],
+                                  slope, _p(chan_mul), _p(red[0]), _p(red[1]), _p(red[2]), _p(red[3]), _p(ws), splits, _st())
+    else:                                            # libs/functions.py:144-147: no batch-statistics terms, zero affine gradients
+        red = torch.zeros(4, c, device=dev)
     dx = empty_nhwc(n, c, h, w, dev)
     dres = empty_nhwc(n, c, h, w, dev) if want_dres else None
     L.skd_abn_bwd_dx_nhwc(P, c, h * w, _p(x), _p(out), _p(dout), _p(dx), _p(dres), _p(stats[0]), _p(stats[1]), _p(weight),

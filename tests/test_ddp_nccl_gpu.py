@@ -1,0 +1,73 @@
+"""Data-parallel semantics over NCCL on 2 GPUs (utils/parallel.py:54-63,155: loss per GPU on its shard, mean over GPUs):
+replicas are identical after construction whatever the per-rank RNG state, the all-reduced flat gradient is the SUM of the
+per-rank gradients, and FlatSGD.step applies their MEAN.  Skipped on a single-GPU box (run with `gpurun --gpus 2`)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        from oracle import port as oport
+        from structure_knowledge_distillation_b200.networks.kd_model import NetModel
+        from structure_knowledge_distillation_b200.utils.train_options import make_args
+        torch.manual_seed(100 + rank)                                  # DIFFERENT init per rank: NetModel must broadcast rank 0's
+        m = NetModel(make_args(batch_size=1, pi=True, pa=True, ho=True, adv_loss_type="hinge", gpu_num=world))
+        p0 = m.G_solver.flat_p.clone(); d0 = m.D_solver.flat_p.clone()
+        gathered = [torch.empty_like(p0) for _ in range(world)]
+        dist.all_gather(gathered, p0)
+        assert all(torch.equal(g, gathered[0]) for g in gathered), "student replicas differ after construction"
+        gathered_d = [torch.empty_like(d0) for _ in range(world)]
+        dist.all_gather(gathered_d, d0)
+        assert all(torch.equal(g, gathered_d[0]) for g in gathered_d), "discriminator replicas differ after construction"
+        u = m.D_model.l1[0].module.weight_u.detach().clone()
+        gu = [torch.empty_like(u) for _ in range(world)]
+        dist.all_gather(gu, u)
+        assert all(torch.equal(g, gu[0]) for g in gu), "spectral-norm vectors differ after construction"
+        images, labels = oport.synthetic_batch(1, 512, 512, seed=7 + rank)          # each rank its own shard
+        m.set_input((images, labels, None, None))
+        m._student_phase()
+        local = m.G_solver.flat_g.clone()
+        m.G_solver.all_reduce_grads(world)
+        summed = m.G_solver.flat_g.clone()
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        ref_sum = sum(parts)
+        err = float((summed - ref_sum).norm() / ref_sum.norm())
+        assert err < 1e-6, err
+        lr, mom, wd = m.G_solver.param_groups[0]["lr"], 0.9, m.args.weight_decay
+        m.G_solver.step()
+        expect = p0 - lr * (ref_sum / world + wd * p0)                               # first step: momentum buffer is zero
+        err2 = float((m.G_solver.flat_p - expect).norm() / (lr * (ref_sum / world + wd * p0)).norm())
+        assert err2 < 1e-5, err2
+        m.discriminator_backward()
+        pd = m.D_solver.flat_p.clone()
+        gd = [torch.empty_like(pd) for _ in range(world)]
+        dist.all_gather(gd, pd)
+        assert all(torch.equal(g, gd[0]) for g in gd), "discriminator replicas diverged after one step"
+        if rank == 0:
+            out.put(("ok", err, err2))
+    except Exception as e:                                              # noqa: BLE001
+        out.put(("fail", rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_nccl_gradient_average_through_flat_sgd():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    mp.spawn(_worker, args=(2, 29533, q), nprocs=2, join=True)
+    res = q.get(timeout=10)
+    print("\nPARITY nccl_dp_world2", res)
+    assert res[0] == "ok", res

@@ -250,9 +250,13 @@ def test_discriminator_wgangp_matches_reference_golden():
     rep = dict(out=rel(o_s[0], gold["out_s"]), p1=rel(o_s[1][:, :4, :8], gold["p1"]), adv=rel(adv, gold["adv"]), gp=rel(gp, gold["gp"]),
                u1=rel(D.l1[0].module.weight_u, gold["u1"]), bn_rm=rel(D.preprocess_additional.running_mean, gold["bn_rm"]))
     worst_n, worst_s = (0.0, None), (0.0, None)
+    top = max(gd["norm"] for gd in gold["grads"].values())
     for name, p in D.named_parameters():
         gd = gold["grads"].get(name)
-        if gd is None or gd["norm"] < 1e-9:
+        # gradients that cancel analytically (e.g. attn2.value_conv.bias: d out / d (last conv input) does not depend on the input, so
+        # the -mean D(T) and +mean D(S) terms cancel exactly and the penalty's tangent carries no bias) are round-off in the
+        # reference's fp32 run too: compared only when they carry signal
+        if gd is None or gd["norm"] < 1e-5 * top:
             continue
         mine = p.grad.detach().flatten().double().cpu()
         en = abs(float(mine.norm()) - gd["norm"]) / gd["norm"]
@@ -332,9 +336,10 @@ def test_discriminator_step_vs_port_autograd(shape, adv):
     if hasattr(Dq, "last_conv"):
         refs["last.0.weight"], refs["last.0.bias"] = Dq.last_conv.weight, Dq.last_conv.bias
     worst = (0.0, None)
+    top = max(float(q.grad.norm()) for q in refs.values() if q.grad is not None)
     for name, p in D.named_parameters():
         q = refs.get(name)
-        if q is None or q.grad is None or float(q.grad.norm()) < 1e-9:
+        if q is None or q.grad is None or float(q.grad.norm()) < 1e-5 * top:       # analytically cancelling gradients: round-off only
             continue
         worst = max(worst, (rel(p.grad, q.grad), name))
     print("\nPARITY discriminator_vs_port", shape, adv, "loss %.2e worst grad rel-L2 %.2e (%s)" % (rel(loss, ref), worst[0], worst[1]))

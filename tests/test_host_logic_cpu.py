@@ -61,9 +61,13 @@ def test_criterion_api_errors_match_reference():
         C.CriterionPixelWise()([torch.zeros(1, 19, 4, 4)], [torch.zeros(1, 19, 4, 5)])
     assert C.CriterionPairWise is C.CriterionPairWiseforWholeFeatAfterPool
     d = [torch.tensor([[0.5, -2.0]])]; t = [torch.tensor([[1.5, 0.25]])]
-    assert abs(float(C.CriterionAdv("hinge")(d, t)) - (0.375 + 0.75)) < 1e-6       # relu(1-T).mean + relu(1+S).mean
-    assert abs(float(C.CriterionAdv("wgan-gp")(d, t)) - (-0.875 + -0.75)) < 1e-6
-    assert abs(float(C.CriterionAdvForG("hinge")(d, d)) - 0.75) < 1e-6
+    with pytest.raises(AssertionError):
+        C.CriterionAdv("hinge")(d, [torch.zeros(1, 3)])
+    # the adversarial criteria are CUDA kernels (values checked on the GPU: tests/test_discriminator_gpu.py); no CPU fallback
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        C.CriterionAdv("hinge")(d, t)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        C.CriterionAdvForG("hinge")(d, d)
 
 
 def test_args_and_lr_poly():
@@ -117,3 +121,55 @@ def test_flat_gradient_allreduce_gloo_world2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_checkpoint_loaders_follow_reference_semantics(tmp_path):
+    """utils/utils.py:73-151: teacher key remap, ImageNet key intersection, S/D resume from <dir>/model_best.pth.tar with the
+    DataParallel 'module.' prefix stripped and last_step / start_epoch / best_mean_IU written back into args."""
+    import argparse
+    import numpy as np
+    from structure_knowledge_distillation_b200.networks.pspnet_combine import BasicBlock, Res_pspnet
+    from structure_knowledge_distillation_b200.networks.sagan_models import Discriminator
+    from structure_knowledge_distillation_b200.utils import utils as U
+    torch.manual_seed(0)
+    src = Res_pspnet(BasicBlock, [2, 2, 2, 2], 19)
+    sd = {"module." + k: v.clone() for k, v in src.state_dict().items()}
+    sdir = tmp_path / "S"; sdir.mkdir()
+    torch.save(dict(step=1234, epoch=5, best_mean_IU=0.61, IU_array=np.arange(19, dtype=np.float64), state_dict=sd), str(sdir / "model_best.pth.tar"))
+    args = argparse.Namespace(S_ckpt_path=str(sdir), S_resume=True, is_student_load_imgnet=False, student_pretrain_model_imgnet="None",
+                              D_ckpt_path=str(tmp_path / "D"), D_resume=True, last_step=0, start_epoch=0, best_mean_IU=0.0)
+    dst = Res_pspnet(BasicBlock, [2, 2, 2, 2], 19)
+    assert U.load_S_model(args, dst, False) == "resume"
+    assert (args.last_step, args.start_epoch, args.best_mean_IU) == (1234, 5, 0.61)
+    assert all(torch.equal(a, b) for a, b in zip(dst.state_dict().values(), src.state_dict().values()))
+    # ImageNet initialisation: only the intersecting keys are taken, the flag wins over S_resume
+    inet = {k: v.clone() + 1 for k, v in src.state_dict().items() if k.startswith("layer1.")}
+    inet["fc.weight"] = torch.zeros(3)
+    torch.save(inet, str(tmp_path / "inet.pth"))
+    args.is_student_load_imgnet, args.student_pretrain_model_imgnet = True, str(tmp_path / "inet.pth")
+    dst2 = Res_pspnet(BasicBlock, [2, 2, 2, 2], 19)
+    before = dst2.state_dict()["conv1.weight"].clone()
+    assert U.load_S_model(args, dst2, False) == "imagenet"
+    assert torch.equal(dst2.state_dict()["layer1.0.conv1.weight"], inet["layer1.0.conv1.weight"]) and torch.equal(dst2.state_dict()["conv1.weight"], before)
+    # discriminator resume (creates the directory, no file yet -> nothing loaded; then with a file)
+    D = Discriminator(1, 19, 8, 65, 64)
+    assert U.load_D_model(args, D, False) is None and os.path.isdir(args.D_ckpt_path)
+    torch.save(dict(epoch=7, best_mean_IU=0.5, state_dict={"module." + k: v for k, v in D.state_dict().items()}), os.path.join(args.D_ckpt_path, "model_best.pth.tar"))
+    D2 = Discriminator(1, 19, 8, 65, 64)
+    assert U.load_D_model(args, D2, False) == "resume" and args.start_epoch == 7
+    assert torch.equal(D2.l1[0].module.weight_u, D.l1[0].module.weight_u)
+    # teacher remap (utils.py:78-87)
+    t_sd = {}
+    for k, v in src.state_dict().items():
+        if k.startswith("pspmodule."):
+            t_sd["head.0." + k[len("pspmodule."):]] = v
+        elif k.startswith("head."):
+            t_sd["head.1." + k[len("head."):]] = v
+        else:
+            t_sd[k] = v
+    t_sd["fc.bias"] = torch.zeros(2)
+    torch.save(t_sd, str(tmp_path / "teacher.pth"))
+    dst3 = Res_pspnet(BasicBlock, [2, 2, 2, 2], 19)
+    assert U.load_T_model(dst3, str(tmp_path / "teacher.pth"))
+    assert torch.equal(dst3.state_dict()["pspmodule.bottleneck.0.weight"], src.state_dict()["pspmodule.bottleneck.0.weight"])
+    assert not U.load_T_model(dst3, str(tmp_path / "missing.pth"))

@@ -107,6 +107,27 @@ def test_activation_abi(L):
         assert torch.allclose(e, F.elu(x), rtol=1e-6, atol=1e-7)
         e2 = e.clone(); L.skd_elu_inv_cuda(n, e2.data_ptr(), _st())
         assert torch.allclose(e2, x, rtol=1e-4, atol=1e-5)
+        # elu backward (bn.cu:348-362): dx *= (x_out + 1) where the OUTPUT is negative -- against torch and the reference's own kernel
+        d = torch.randn(n, device="cuda", generator=g); d0 = d.clone()
+        L.skd_elu_backward_cuda(n, e.data_ptr(), d.data_ptr(), _st())
+        assert torch.allclose(d, torch.where(e < 0, d0 * (e + 1.0), d0), rtol=1e-6, atol=1e-7)
+        ref = _ref_bn()
+        if ref is not None:
+            vp = ctypes.c_void_p
+            for name, mine, args in (("_elu_backward_cuda", L.skd_elu_backward_cuda, 2), ("_leaky_relu_backward_cuda", L.skd_leaky_relu_backward_cuda, 3)):
+                fn = getattr(ref, name)
+                fn.restype = ctypes.c_int
+                d1, d2 = d0.clone(), d0.clone()
+                if args == 2:
+                    fn.argtypes = [ctypes.c_int, vp, vp, vp]
+                    assert fn(n, e.data_ptr(), d1.data_ptr(), _st()) == 1
+                    mine(n, e.data_ptr(), d2.data_ptr(), _st())
+                else:
+                    fn.argtypes = [ctypes.c_int, vp, vp, ctypes.c_float, vp]
+                    assert fn(n, y.data_ptr(), d1.data_ptr(), 0.01, _st()) == 1
+                    mine(n, y.data_ptr(), d2.data_ptr(), 0.01, _st())
+                torch.cuda.synchronize()
+                assert torch.equal(d1, d2), name
 
 
 # ---------------------------------------------------------------------------------------------- ABN, fused NHWC path
@@ -207,6 +228,33 @@ def test_pairwise_unpooled_tcgen05_vs_oracle(ops, n, cs, ct, h, w):
     finally:
         Fn.PairWiseLoss.TCGEN05_MIN_NODES = old
     assert abs(float(l2) - float(ref)) / float(ref) < 2e-5
+
+
+def test_pairwise_affinity_full_size_north_star_shape():
+    """The north-star affinity shape -- batch 8, student 128 / teacher 512 channels, 65x129 map, pool_scale 1/65 -> 8 385 nodes,
+    8 385 x 8 385 x 640 per image on tcgen05 -- loss and gradient against oracle/port.pairwise_loss evaluated in float64 on the
+    GPU (per image, to bound memory).  TF32 operands: 1e-3 on the loss, 1e-2 rel-L2 on the gradient."""
+    from oracle import port
+    from structure_knowledge_distillation_b200.utils.criterion import CriterionPairWiseforWholeFeatAfterPool
+    g = torch.Generator(device="cuda").manual_seed(65129)
+    n, cs, ct, h, w = 8, 128, 512, 65, 129
+    fS = (torch.randn(n, cs, h, w, device="cuda", generator=g) + 0.5).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    fT = (torch.randn(n, ct, h, w, device="cuda", generator=g) + 0.5).contiguous(memory_format=torch.channels_last)
+    crit = CriterionPairWiseforWholeFeatAfterPool(scale=1.0 / 65, feat_ind=-5)
+    S = [None, None, fS, None, None, None, None]; T = [None, None, fT, None, None, None, None]
+    loss = crit(S, T)
+    loss.backward()
+    ref_total, grads = 0.0, []
+    for i in range(n):                                                     # sum over images of sum (A_T - A_S)^2 / nodes^2, then / N
+        s = fS.detach()[i:i + 1].double().contiguous().requires_grad_(True)
+        r = port.pairwise_loss(s, fT[i:i + 1].double().contiguous(), 1.0 / 65) / n
+        (gi,) = torch.autograd.grad(r, s)
+        ref_total += float(r); grads.append(gi)
+    gref = torch.cat(grads)
+    e_loss = abs(float(loss) - ref_total) / ref_total
+    e_grad = rel(fS.grad, gref)
+    print("\nPARITY pairwise_8385_nodes loss %.2e grad rel-L2 %.2e" % (e_loss, e_grad))
+    assert e_loss < 1e-3 and e_grad < 1e-2
 
 
 def test_pixelwise_full_size_properties(ops):
