@@ -92,6 +92,7 @@ class NetModel():
         self.best_mean_IU = _arg(args, "best_mean_IU", 0.0)
         if self.world > 1:
             self._sync_replicas()
+            self.G_solver.enable_overlap(_arg(args, "allreduce_buckets", 4))
 
         self.criterion = CriterionDSN()
         self.criterion_pixel_wise = CriterionPixelWise()
@@ -170,17 +171,30 @@ class NetModel():
         # the generator step only needs d D(S) / d logits: the reference's D gradients of this pass are discarded by
         # D_solver.zero_grad() (kd_model.py:154), so they are not computed
         self.D_model.skip_param_grads = True
+        overlap = self.world > 1 and self.G_solver._buckets is not None
+        if overlap:
+            # the ONE collective of the path (teacher frozen): bucketed NCCL all-reduce of the flat student gradient, issued from
+            # inside the backward pass as each range of parameters completes (utils/parallel.py:54-63,155 semantics: mean over ranks)
+            self.G_solver.begin_overlapped_reduce(self.world)
         try:
             G_loss.backward()
         finally:
             self.D_model.skip_param_grads = False
             self.D_model.engine.release()
+            if overlap:
+                self.G_solver.finish_overlapped_reduce()
+        self._g_reduced = overlap
         self.G_loss = _LazyScalar(G_loss)
 
     def discriminator_backward(self):
         self._discriminator_phase()
         self.D_solver.all_reduce_grads(self.world)
         self.D_solver.step()
+
+    def _reduce_G(self):
+        """all-reduce of the student gradient unless the backward pass already did it bucket by bucket"""
+        if not getattr(self, "_g_reduced", False):
+            self.G_solver.all_reduce_grads(self.world)
 
     def _student_phase(self):
         self.forward()
@@ -210,7 +224,7 @@ class NetModel():
         if self._graphs is not None:
             return self._optimize_graphed()
         self._student_phase()
-        self.G_solver.all_reduce_grads(self.world)       # the one collective of the path (teacher is frozen)
+        self._reduce_G()
         self.G_solver.step()
         if self.args.ho == True:
             self.discriminator_backward()
@@ -233,7 +247,7 @@ class NetModel():
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
                     self._student_phase()
-                    self.G_solver.all_reduce_grads(self.world); self.G_solver.step()
+                    self._reduce_G(); self.G_solver.step()
                     if self.args.ho == True:
                         self._discriminator_phase()
                         self.D_solver.all_reduce_grads(self.world); self.D_solver.step()
@@ -245,7 +259,7 @@ class NetModel():
             g["student"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g["student"]):
                 self._student_phase()
-            self.G_solver.all_reduce_grads(self.world); self.G_solver.step()
+            self._reduce_G(); self.G_solver.step()
             if self.args.ho == True:
                 g["D"] = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g["D"], pool=g["student"].pool()):
@@ -254,7 +268,7 @@ class NetModel():
             g["captured"] = True
             return
         g["student"].replay()
-        self.G_solver.all_reduce_grads(self.world); self.G_solver.step()
+        self._reduce_G(); self.G_solver.step()
         if self.args.ho == True:
             g["D"].replay()
             self.D_solver.all_reduce_grads(self.world); self.D_solver.step()

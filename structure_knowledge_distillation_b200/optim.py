@@ -52,6 +52,8 @@ class FlatSGD:
         self.lr_dev = torch.tensor(float(lr), device=dev, dtype=torch.float32)
         self.steps = 0
         self.grad_scale = 1.0
+        self._offsets = offs + [total]
+        self._buckets = None
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
@@ -66,6 +68,63 @@ class FlatSGD:
             self.grad_scale = 1.0 / world
         else:
             self.grad_scale = 1.0
+
+    # ---- all-reduce overlapped with the backward pass -------------------------------------------------------------------------
+    def enable_overlap(self, n_buckets=4):
+        """Split the flat gradient into `n_buckets` contiguous ranges of whole parameters (forward order).  During backward a
+        post-accumulate hook counts the parameters of each range; when a range is complete its NCCL all-reduce is issued on a side
+        stream -- the ranges of the late layers (finished first) travel while the early layers are still being differentiated.
+        CUDA-graph capturable: the side stream forks from / joins the capturing stream."""
+        n = len(self.params)
+        total = self._offsets[-1]
+        bounds, target, nxt = [0], total / n_buckets, 1
+        for i in range(n):
+            if self._offsets[i + 1] >= target * nxt and len(bounds) < n_buckets:
+                bounds.append(i + 1); nxt += 1
+        if bounds[-1] != n:
+            bounds.append(n)
+        self._buckets = [dict(lo=lo, hi=hi, start=self._offsets[lo], end=self._offsets[hi], left=0, sent=False)
+                         for lo, hi in zip(bounds[:-1], bounds[1:]) if hi > lo]
+        which = {}
+        for bi, b in enumerate(self._buckets):
+            for i in range(b["lo"], b["hi"]):
+                which[i] = bi
+        self._side = torch.cuda.Stream()
+        self._active = False
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(lambda _p, bi=which[i]: self._arrived(bi))
+
+    def begin_overlapped_reduce(self, world):
+        self._world = world
+        self.grad_scale = 1.0 / world if world > 1 else 1.0
+        for b in self._buckets:
+            b["left"], b["sent"] = b["hi"] - b["lo"], False
+        self._active = world > 1
+
+    def _send(self, b):
+        b["sent"] = True
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)                                  # the bucket's gradients are complete on the compute stream
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.flat_g[b["start"]:b["end"]], op=dist.ReduceOp.SUM)
+
+    def _arrived(self, bi):
+        if not self._active:
+            return
+        b = self._buckets[bi]
+        b["left"] -= 1
+        if b["left"] == 0 and not b["sent"]:
+            self._send(b)
+
+    def finish_overlapped_reduce(self):
+        """Reduce whatever has not been sent (parameters that received no gradient) and join the side stream."""
+        if not self._active:
+            return
+        for b in self._buckets:
+            if not b["sent"]:
+                self._send(b)
+        torch.cuda.current_stream().wait_stream(self._side)
+        self._active = False
 
     def step(self):
         g = self.param_groups[0]

@@ -33,6 +33,11 @@ def _worker(rank, world, port, out):
         assert all(torch.equal(g, gu[0]) for g in gu), "spectral-norm vectors differ after construction"
         images, labels = oport.synthetic_batch(1, 512, 512, seed=7 + rank)          # each rank its own shard
         m.set_input((images, labels, None, None))
+        for drop in m.student.dropouts():                                           # fixed Dropout2d masks: the two passes below must agree
+            drop.injected = (torch.rand(1, 128, generator=torch.Generator().manual_seed(5 + rank)) >= 0.1).float()
+        buckets, m.G_solver._buckets = m.G_solver._buckets, None                     # first pass: plain (un-overlapped) exchange
+        assert buckets is not None and len(buckets) >= 2
+        d_state = {k: v.clone() for k, v in m.D_model.state_dict().items()}         # D(S) advances the spectral-norm vectors / BN stats
         m._student_phase()
         local = m.G_solver.flat_g.clone()
         m.G_solver.all_reduce_grads(world)
@@ -42,6 +47,15 @@ def _worker(rank, world, port, out):
         ref_sum = sum(parts)
         err = float((summed - ref_sum).norm() / ref_sum.norm())
         assert err < 1e-6, err
+        # second pass over the same weights / inputs with the bucketed all-reduce issued from inside backward: same sums, bit for bit
+        m.G_solver._buckets = buckets
+        with torch.no_grad():
+            for k, v in m.D_model.state_dict().items():
+                v.copy_(d_state[k])
+        m._student_phase()
+        assert m._g_reduced
+        torch.cuda.synchronize()
+        assert torch.equal(m.G_solver.flat_g, summed), float((m.G_solver.flat_g - summed).abs().max())
         lr, mom, wd = m.G_solver.param_groups[0]["lr"], 0.9, m.args.weight_decay
         m.G_solver.step()
         expect = p0 - lr * (ref_sum / world + wd * p0)                               # first step: momentum buffer is zero
