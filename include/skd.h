@@ -61,14 +61,18 @@ int skd_abn_fold(int C, const float* mean, const float* var, const float* weight
 int skd_abn_apply_nhwc(long long P, int C, int S, const float* x, float* out, int out_pitch, const float* scale,
                        const float* shift, int act, float slope, const float* residual, const float* chan_mul,
                        int round_tf32, cudaStream_t);
-/* edz, eydz (means) and dweight=sign(w)*sum(y*dz), dbias=sum(dz) (bn.cu:214-230); dz = dout*chan_mul*act'(out) */
+/* edz, eydz (means) and dweight=sign(w)*sum(y*dz), dbias=sum(dz) (bn.cu:214-230); dz = dout*chan_mul*act'(out).
+   out may be NULL for sign-only activations without a fused residual (none / relu / leaky): the sign is then recomputed from
+   x*scale + shift (the apply pass's own FMA) and the stored activation output is never read. */
 int skd_abn_bwd_reduce_nhwc(long long P, int C, int S, const float* x, const float* out, const float* dout, const float* mean,
                             const float* var, const float* weight, float eps, int act, float slope, const float* chan_mul,
-                            float* edz, float* eydz, float* dweight, float* dbias, float* workspace, int splits, cudaStream_t);
+                            float* edz, float* eydz, float* dweight, float* dbias, float* workspace, int splits,
+                            const float* scale, const float* shift, cudaStream_t);
 /* dx = (dz - edz - y*eydz)*(|w|+eps)*rsqrt(var+eps); dres = dz (gradient of the residual input), either may be NULL... dx not */
 int skd_abn_bwd_dx_nhwc(long long P, int C, int S, const float* x, const float* out, const float* dout, float* dx, float* dres,
                         const float* mean, const float* var, const float* weight, const float* edz, const float* eydz,
-                        float eps, int act, float slope, const float* chan_mul, int round_tf32, cudaStream_t);
+                        float eps, int act, float slope, const float* chan_mul, int round_tf32, const float* scale,
+                        const float* shift, cudaStream_t);
 
 /* ---- C. losses ---- */
 int skd_loss_max_partials(void);              /* doubles of workspace the reductions below may use (x2 for dsn_ce) */

@@ -407,7 +407,10 @@ __global__ void __launch_bounds__(256)
 nhwc_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ out, const float* __restrict__ dout,
                         float2* __restrict__ partial, long long P, int C, int S, const float* __restrict__ mean,
                         const float* __restrict__ var, float eps, int act, float slope,
-                        const float* __restrict__ chan_mul) {
+                        const float* __restrict__ chan_mul, const float* __restrict__ scale, const float* __restrict__ shift) {
+  // out == nullptr: the activation's sign is recomputed as x*scale + shift -- the very FMA the apply pass evaluated, so the mask
+  // is bit-identical -- and the stored activation output is not read at all (layers without a fused residual: 4 reads instead of 6
+  // over the two backward passes)
   __shared__ float4 sh1[256], sh2[256];
   const int C4 = C >> 2;
   const int TC = C4 < 256 ? C4 : 256;
@@ -420,13 +423,17 @@ nhwc_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ o
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
     float4 is = __ldg(reinterpret_cast<const float4*>(var) + c4);
     is.x = 1.f / sqrtf(is.x + eps); is.y = 1.f / sqrtf(is.y + eps); is.z = 1.f / sqrtf(is.z + eps); is.w = 1.f / sqrtf(is.w + eps);
+    float4 sc = make_float4(0, 0, 0, 0), sf = sc;
+    if (!out) { sc = __ldg(reinterpret_cast<const float4*>(scale) + c4); sf = __ldg(reinterpret_cast<const float4*>(shift) + c4); }
     const long long rows_per = (P + gridDim.x - 1) / gridDim.x;
     const long long r0 = (long long)blockIdx.x * rows_per;
     long long r1 = r0 + rows_per; if (r1 > P) r1 = P;
     for (long long r = r0 + ty; r < r1; r += TR) {
       const long long i = r * C4 + c4;
       float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + i);
-      float4 ov = ld_stream(reinterpret_cast<const float4*>(out) + i);
+      float4 ov;
+      if (out) ov = ld_stream(reinterpret_cast<const float4*>(out) + i);
+      else { ov.x = xv.x * sc.x + sf.x; ov.y = xv.y * sc.y + sf.y; ov.z = xv.z * sc.z + sf.z; ov.w = xv.w * sc.w + sf.w; }
       float4 g = ld_stream(reinterpret_cast<const float4*>(dout) + i);
       if (chan_mul) {
         const float4 m = __ldg(reinterpret_cast<const float4*>(chan_mul) + (r / S) * C4 + c4);
@@ -477,12 +484,17 @@ nhwc_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ out, c
                    float* __restrict__ dx, float* __restrict__ dres, long long total4, int C4, int S,
                    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ weight,
                    const float* __restrict__ edz, const float* __restrict__ eydz, float eps, int act, float slope,
-                   const float* __restrict__ chan_mul, int round_out) {
+                   const float* __restrict__ chan_mul, int round_out, const float* __restrict__ scale, const float* __restrict__ shift) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / C4;
     const int c4 = (int)(i - row * C4);
     float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + i);
-    float4 ov = ld_stream(reinterpret_cast<const float4*>(out) + i);
+    float4 ov;
+    if (out) ov = ld_stream(reinterpret_cast<const float4*>(out) + i);
+    else {                                                  // sign of the activation input, recomputed (see nhwc_bwd_partial_kernel)
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4), sf = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+      ov.x = xv.x * sc.x + sf.x; ov.y = xv.y * sc.y + sf.y; ov.z = xv.z * sc.z + sf.z; ov.w = xv.w * sc.w + sf.w;
+    }
     float4 g = ld_stream(reinterpret_cast<const float4*>(dout) + i);
     if (chan_mul) {
       const float4 m = __ldg(reinterpret_cast<const float4*>(chan_mul) + (row / S) * C4 + c4);
@@ -622,12 +634,14 @@ extern "C" int skd_abn_apply_nhwc(long long P, int C, int S, const float* x, flo
 extern "C" int skd_abn_bwd_reduce_nhwc(long long P, int C, int S, const float* x, const float* out, const float* dout,
                                        const float* mean, const float* var, const float* weight, float eps, int act,
                                        float slope, const float* chan_mul, float* edz, float* eydz, float* dweight,
-                                       float* dbias, float* workspace, int splits, cudaStream_t st) {
+                                       float* dbias, float* workspace, int splits, const float* scale, const float* shift,
+                                       cudaStream_t st) {
   if (!nhwc_check("skd_abn_bwd_reduce_nhwc", C, x, out, dout)) return 0;
+  if (!out && (!scale || !shift || act == ACT_ELU)) { set_error_msg("skd_abn_bwd_reduce_nhwc", "out == NULL needs scale/shift and a sign-only activation"); return 0; }
   if (P <= 0) return 1;
   const int chunks = (C / 4 + 255) / 256;
   nhwc_bwd_partial_kernel<<<dim3(splits, chunks), 256, 0, st>>>(x, out, dout, reinterpret_cast<float2*>(workspace), P, C, S,
-                                                               mean, var, eps, act, slope, chan_mul);
+                                                               mean, var, eps, act, slope, chan_mul, scale, shift);
   nhwc_bwd_finalize_kernel<<<(C + 31) / 32, 512, 0, st>>>(reinterpret_cast<const float2*>(workspace), splits, C, (float)P,
                                                            weight, edz, eydz, dweight, dbias);
   return finish("skd_abn_bwd_reduce_nhwc", 2);
@@ -636,11 +650,12 @@ extern "C" int skd_abn_bwd_reduce_nhwc(long long P, int C, int S, const float* x
 extern "C" int skd_abn_bwd_dx_nhwc(long long P, int C, int S, const float* x, const float* out, const float* dout,
                                    float* dx, float* dres, const float* mean, const float* var, const float* weight,
                                    const float* edz, const float* eydz, float eps, int act, float slope,
-                                   const float* chan_mul, int round_tf32, cudaStream_t st) {
+                                   const float* chan_mul, int round_tf32, const float* scale, const float* shift, cudaStream_t st) {
   if (!nhwc_check("skd_abn_bwd_dx_nhwc", C, x, dx, dres)) return 0;
+  if (!out && (!scale || !shift || act == ACT_ELU)) { set_error_msg("skd_abn_bwd_dx_nhwc", "out == NULL needs scale/shift and a sign-only activation"); return 0; }
   if (P <= 0) return 1;
   const long long total4 = P * (C / 4);
   nhwc_bwd_dx_kernel<<<ew_blocks(total4), 256, 0, st>>>(x, out, dout, dx, dres, total4, C / 4, S, mean, var, weight, edz,
-                                                       eydz, eps, act, slope, chan_mul, round_tf32);
+                                                       eydz, eps, act, slope, chan_mul, round_tf32, scale, shift);
   return finish("skd_abn_bwd_dx_nhwc");
 }

@@ -173,68 +173,61 @@ dsn_ce_fwd_kernel(const float* __restrict__ L0, const float* __restrict__ L1, St
 }
 
 // Backward, phase 1: for one output row Y of one image: G[c][X] = softmax - onehot (0 if ignored), then reduce along
-// X into the w source columns:  T1[n][Y][c][x] = sum_X wx(x;X) G[c][X].   One block per (Y, n, head).
+// X into the w source columns:  T1[n][Y][x][c] = sum_X wx(x;X) G[c][X].   One block per (Y, n, head).
+// The X that feed source column x are contiguous runs (i0 is monotonic in X): those with i0 == x (weight wa = l0, plus l1 where
+// the right neighbour is clamped onto the same column) and those with i0 == x-1 (weight wb = l1).  The run starts first[x] are
+// found once per chunk, so a (x, c) pair is ~2*W/w shared-memory FMAs.  Lanes run over c (odd row pitch: conflict-free).
 __global__ void __launch_bounds__(1024)
 dsn_ce_bwd_rows_kernel(const float* __restrict__ L0, const float* __restrict__ L1, Strides s0, Strides s1,
                        const long long* __restrict__ labels, int N, int C, int h, int w, int H, int W, int ignore,
                        float* __restrict__ T1, int chunk) {
-  extern __shared__ float G[];                                 // [C][chunk]
+  extern __shared__ float G[];                                 // [C][chunk|1], wa[chunk], wb[chunk], first[w+1]
+  const int pitch = chunk | 1;
+  float* wa = G + (size_t)C * pitch;
+  float* wb = wa + chunk;
+  int* first = reinterpret_cast<int*>(wb + chunk);
   const int Y = blockIdx.x, n = blockIdx.y, head = blockIdx.z;
   const float* L = head == 0 ? L0 : L1;
   const Strides st = head == 0 ? s0 : s1;
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
   const Bilin by = bilin(Y, sy, h);
   float* out = T1 + (((size_t)head * N + n) * H + Y) * (size_t)C * w;
-  // each (x, c) pair keeps its accumulator in a register across the X chunks
-  constexpr int kMaxPairs = 4;
-  float acc[kMaxPairs];
-#pragma unroll
-  for (int k = 0; k < kMaxPairs; ++k) acc[k] = 0.f;
   for (int X0 = 0; X0 < W; X0 += chunk) {
     const int X1 = min(W, X0 + chunk);
     __syncthreads();
+    for (int x = threadIdx.x; x <= w; x += blockDim.x) first[x] = X1 - X0;
+    __syncthreads();
     for (int X = X0 + threadIdx.x; X < X1; X += blockDim.x) {
       const long long lab = labels[((long long)n * H + Y) * W + X];
+      const Bilin bx = bilin(X, sx, w);
+      const int j = X - X0;
+      wa[j] = bx.l0 + (bx.i1 == bx.i0 ? bx.l1 : 0.f);
+      wb[j] = bx.i1 == bx.i0 ? 0.f : bx.l1;
+      const int prev = X == X0 ? -1 : bilin(X - 1, sx, w).i0;
+      for (int x = prev + 1; x <= bx.i0; ++x) first[x] = j;     // first X of the chunk with i0 >= x
       float v[kMaxClasses];
       if (lab == ignore) {
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) if (c < C) G[c * chunk + (X - X0)] = 0.f;
+        for (int c = 0; c < kMaxClasses; ++c) if (c < C) G[c * pitch + j] = 0.f;
       } else {
-        const Bilin bx = bilin(X, sx, w);
         const float lse = up_logits(L, st, n, C, w, by, bx, v);
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) if (c < C) G[c * chunk + (X - X0)] = __expf(v[c] - lse) - (c == (int)lab ? 1.f : 0.f);
+        for (int c = 0; c < kMaxClasses; ++c) if (c < C) G[c * pitch + j] = __expf(v[c] - lse) - (c == (int)lab ? 1.f : 0.f);
       }
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kMaxPairs; ++k) {
-      const int pair = threadIdx.x + k * blockDim.x;
-      if (pair < C * w) {
-        const int c = pair / w, x = pair - c * w;
-        // contributing X: those whose i0 == x (weight l0) or i1 == x (weight l1): X in ((x-1)/sx, (x+1)/sx)
-        int lo = sx > 0.f ? (int)floorf((float)(x - 1) / sx) : 0, hi = sx > 0.f ? (int)ceilf((float)(x + 1) / sx) : W - 1;
-        lo = max(lo - 1, X0); hi = min(hi + 1, X1 - 1);
-        float a = 0.f;
-        for (int X = lo; X <= hi; ++X) {
-          const Bilin bx = bilin(X, sx, w);
-          float wgt = 0.f;
-          if (bx.i0 == x) wgt += bx.l0;
-          if (bx.i1 == x) wgt += bx.l1;
-          a += wgt * G[c * chunk + (X - X0)];
-        }
-        acc[k] += a;
-      }
+    for (int pair = threadIdx.x; pair < C * w; pair += blockDim.x) {
+      const int x = pair / C, c = pair - x * C;
+      const float* g = G + c * pitch;
+      float a = 0.f;
+      for (int j = first[x]; j < first[x + 1]; ++j) a += wa[j] * g[j];
+      if (x > 0) for (int j = first[x - 1]; j < first[x]; ++j) a += wb[j] * g[j];
+      if (X0 == 0) out[pair] = a; else out[pair] += a;
     }
-  }
-#pragma unroll
-  for (int k = 0; k < kMaxPairs; ++k) {
-    const int pair = threadIdx.x + k * blockDim.x;
-    if (pair < C * w) out[pair] = acc[k];
   }
 }
 
-// Backward, phase 2: dL[n][c][y][x] = g*wh/count * sum_Y wy(y;Y) T1[n][Y][c][x]
+// Backward, phase 2: dL[n][c][y][x] = g*wh/count * sum_Y wy(y;Y) T1[n][Y][x][c]
 __global__ void __launch_bounds__(256)
 dsn_ce_bwd_cols_kernel(const float* __restrict__ T1, float* __restrict__ d0, float* __restrict__ d1, Strides a0, Strides a1,
                        int N, int C, int h, int w, int H, const float* __restrict__ gout, const float* __restrict__ count,
@@ -245,10 +238,10 @@ dsn_ce_bwd_cols_kernel(const float* __restrict__ T1, float* __restrict__ d0, flo
   const float gc = __ldg(gout) / __ldg(count);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per * heads; i += (long long)gridDim.x * blockDim.x) {
     const int head = (int)(i / per); long long r = i - (long long)head * per;
-    const int x = (int)(r % w); r /= w; const int c = (int)(r % C); r /= C; const int y = (int)(r % h); const int n = (int)(r / h);
+    const int c = (int)(r % C); r /= C; const int x = (int)(r % w); r /= w; const int y = (int)(r % h); const int n = (int)(r / h);
     int lo = sy > 0.f ? (int)floorf((float)(y - 1) / sy) : 0, hi = sy > 0.f ? (int)ceilf((float)(y + 1) / sy) : H - 1;
     lo = max(lo - 1, 0); hi = min(hi + 1, H - 1);
-    const float* src = T1 + (((size_t)head * N + n) * H) * (size_t)C * w + (size_t)c * w + x;
+    const float* src = T1 + (((size_t)head * N + n) * H) * (size_t)C * w + (size_t)x * C + c;
     float a = 0.f;
     for (int Y = lo; Y <= hi; ++Y) {
       const Bilin by = bilin(Y, sy, h);
@@ -459,13 +452,13 @@ extern "C" int skd_dsn_ce_bwd(int N, int C, int h, int w, int H, int W, const fl
                               const long long* labels, int ignore_index, float w0, float w1, const float* grad_out,
                               const float* count, float* d0, float* d1, float* workspace, cudaStream_t st) {
   if (C > kMaxClasses) { set_error_msg("skd_dsn_ce_bwd", "C > 32 classes unsupported"); return 0; }
-  if ((long long)C * w > 4 * 1024) { set_error_msg("skd_dsn_ce_bwd", "C*w > 4096 unsupported"); return 0; }
   const int heads = L1 ? 2 : 1;
   int chunk = W < 1024 ? W : 1024;
-  const size_t smem = (size_t)C * chunk * sizeof(float);
+  const size_t smem = ((size_t)C * (chunk | 1) + 2 * (size_t)chunk + (size_t)w + 2) * sizeof(float);
+  if (smem > 200 * 1024) { set_error_msg("skd_dsn_ce_bwd", "source width too large for one block's shared memory"); return 0; }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * (int)sizeof(float));
+    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
   dsn_ce_bwd_rows_kernel<<<dim3(H, N, heads), 1024, smem, st>>>(L0, L1, Strides{a_sn, a_sc, a_sp}, Strides{b_sn, b_sc, b_sp},

@@ -184,7 +184,10 @@ class ABN(torch.autograd.Function):
             sc, sh = ops.abn_fold(running_mean, running_var, weight, bias, eps)
             st = torch.stack([running_mean, running_var, sc, sh])
         out = ops.abn_apply(x, st[2], st[3], activation, slope, residual=residual, chan_mul=chan_mul)
-        ctx.save_for_backward(x, out, st, weight, chan_mul)
+        # without a fused residual the backward recomputes the activation's sign from x (same FMA as the apply pass): the stored
+        # output is not read again -- two HBM passes fewer per layer
+        ctx.out_saved = residual is not None or activation == "elu"
+        ctx.save_for_backward(x, out if ctx.out_saved else None, st, weight, chan_mul)
         ctx.cfg = (training, eps, activation, slope, residual is not None)
         return out
 

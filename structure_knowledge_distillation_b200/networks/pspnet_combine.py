@@ -136,8 +136,9 @@ class _Dropout2d(nn.Dropout2d):
     def channel_multiplier(self, n, c, device):
         if not self.training or self.p == 0:
             return None
-        keep = self.injected.to(device=device, dtype=torch.float32) if self.injected is not None else \
-            (torch.rand(n, c, device=device) >= self.p).float()
+        if self.injected is not None and (self.injected.device != device or self.injected.dtype != torch.float32):
+            self.injected = self.injected.to(device=device, dtype=torch.float32)     # once: a CUDA-graph capture cannot copy from the host
+        keep = self.injected if self.injected is not None else (torch.rand(n, c, device=device) >= self.p).float()
         return (keep / (1.0 - self.p)).contiguous()
 
 

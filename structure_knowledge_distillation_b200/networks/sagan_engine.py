@@ -274,12 +274,16 @@ class DiscEngine:
                 gh = _f(nb, oh, ow, a["c"], dev=dev)
                 gq_lo = self._split(gqkv)
                 self._conv(1, 1, nb * n, a["ldq"], a["c"], 1, 1, 0, gqkv, gq_lo, a["ldq"], a["wt"], a["wt_lo"], gh, a["c"], residual=g2, ldr=a["c"])
+                if getattr(t, "debug", None) is not None:
+                    t.debug.append(("gy%d" % li, g2.clone())); t.debug.append(("gqkv%d" % li, gqkv.clone())); t.debug.append(("gh%d" % li, gh.clone()))
                 g, masked = gh, False
             if not masked:
                 gz = torch.empty_like(g)
                 per = B * oh * ow * cout
                 L.skd_disc_mask_mul(g.numel(), per, _p(t.h[li]), _p(g), _p(gz), None, LEAK, st)
                 g = gz
+            if getattr(t, "debug", None) is not None:
+                t.debug.append(("gz%d" % li, g.clone()))
             # ---- SN conv: z = conv(hin, w_bar) / sigma + b
             hin = t.h0 if li == 0 else (t.att[li - 1]["y"] if (li - 1) in t.att else t.h[li - 1])
             if param_grads:

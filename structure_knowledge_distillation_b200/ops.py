@@ -131,7 +131,7 @@ def abn_apply(x, scale, shift, act, slope, residual=None, chan_mul=None, out=Non
 def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dres, round_tf32=False, training=True):
     """-> dx, dres (or None), dweight, dbias"""
     n, c, h, w, pitch = nhwc_meta(x)
-    if nhwc_meta(out)[4] != c or nhwc_meta(dout)[4] != c or pitch != c:
+    if (out is not None and nhwc_meta(out)[4] != c) or nhwc_meta(dout)[4] != c or pitch != c:
         raise ValueError("Non-contiguous input")
     P = n * h * w
     L = lib()
@@ -141,13 +141,14 @@ def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dr
     if training:
         red = torch.empty(4, c, device=dev)          # edz, eydz, dweight, dbias
         L.skd_abn_bwd_reduce_nhwc(P, c, h * w, _p(x), _p(out), _p(dout), _p(stats[0]), _p(stats[1]), _p(weight), eps, ACT[act],
-                                  slope, _p(chan_mul), _p(red[0]), _p(red[1]), _p(red[2]), _p(red[3]), _p(ws), splits, _st())
+                                  slope, _p(chan_mul), _p(red[0]), _p(red[1]), _p(red[2]), _p(red[3]), _p(ws), splits, _p(stats[2]), _p(stats[3]),
+                                  _st())
     else:                                            # libs/functions.py:144-147: no batch-statistics terms, zero affine gradients
         red = torch.zeros(4, c, device=dev)
     dx = empty_nhwc(n, c, h, w, dev)
     dres = empty_nhwc(n, c, h, w, dev) if want_dres else None
     L.skd_abn_bwd_dx_nhwc(P, c, h * w, _p(x), _p(out), _p(dout), _p(dx), _p(dres), _p(stats[0]), _p(stats[1]), _p(weight),
-                          _p(red[0]), _p(red[1]), eps, ACT[act], slope, _p(chan_mul), int(round_tf32), _st())
+                          _p(red[0]), _p(red[1]), eps, ACT[act], slope, _p(chan_mul), int(round_tf32), _p(stats[2]), _p(stats[3]), _st())
     return dx, dres, red[2], red[3]
 
 

@@ -89,20 +89,29 @@ def test_distillation_step_matches_reference_golden(name):
     if cfg.ho:
         m.discriminator_backward()
         report["D"] = _relerr(m.D_loss, gold["D"])
-        wd, wdn = 0.0, None
-        dm, dg = [], []
+        # per-tensor comparison.  Gradients that cancel analytically (attention gammas at their zero init: <gy, O> summed over
+        # positions of both signs; last.0.bias: +mean - mean) are round-off residue 3-4 orders below the other tensors in the
+        # reference's own fp32 run, so every denominator is floored at 1e-3 of the largest gradient norm of the step
+        top = max(g["norm"] for g in gold["D_grads"].values())
+        wd, wdn, ws_, wsn, table = 0.0, None, 0.0, None, []
         for pname, p in m.D_model.named_parameters():
             g = gold["D_grads"].get(pname)
-            if g is None or g["norm"] < 1e-7 or p.grad is None:
+            if g is None or p.grad is None:
                 continue
             mine = p.grad.detach().flatten().double()
-            e = abs(float(mine.norm()) - g["norm"]) / g["norm"]
+            floor = 1e-3 * top
+            e = abs(float(mine.norm()) - g["norm"]) / max(g["norm"], floor)
+            gs = g["samples"].double(); ms = mine[g["idx"].to(mine.device)].cpu()
+            # the 16 sampled ELEMENTS: rel-L2 against the samples' own norm (floored at what 16 elements of a floor-sized tensor carry)
+            e_s = float((ms - gs).norm() / max(float(gs.norm()), floor * (len(gs) / max(mine.numel(), len(gs))) ** 0.5))
+            table.append((pname, e, e_s))
             if e > wd:
                 wd, wdn = e, pname
-            dm.append(mine[g["idx"].to(mine.device)].cpu() / g["norm"]); dg.append(g["samples"].double() / g["norm"])
-        dm, dg = torch.cat(dm), torch.cat(dg)
+            if e_s > ws_:
+                ws_, wsn = e_s, pname
         report["worst_D_grad_norm_rel"] = (wd, wdn)
-        report["D_grad_samples_rel_l2"] = float((dm - dg).norm() / dg.norm())
+        report["worst_D_grad_samples_rel_l2"] = (ws_, wsn)
+        report["D_grad_table"] = " ".join("%s:%.1e/%.1e" % (n.replace(".0.module", "").replace("preprocess_additional", "bn"), a, b) for n, a, b in table if a > 0 or b > 0)
     print("\nPARITY", name, {k: (("%.2e" % v) if isinstance(v, float) else v) for k, v in report.items()})
     full = name.startswith("baseline")
     # Contract (BASELINE.json): every loss within 1e-3 relative of the reference -- held at the benchmarked configuration
@@ -124,7 +133,7 @@ def test_distillation_step_matches_reference_golden(name):
     if cfg.ho:
         # D's gradients depend on the student logits (3e-2 rel-L2 on the small random-init cases, 5e-3 at the benchmark config)
         assert report["worst_D_grad_norm_rel"][0] < (0.05 if full else 0.3), report["worst_D_grad_norm_rel"]
-        assert report["D_grad_samples_rel_l2"] < (0.05 if full else 0.3), report["D_grad_samples_rel_l2"]
+        assert report["worst_D_grad_samples_rel_l2"][0] < (0.1 if full else 0.3), report["worst_D_grad_samples_rel_l2"]
 
 
 def _snapshot(m):
