@@ -134,6 +134,24 @@ int skd_split_tf32(long long n, const float* src, float* hi, float* lo, cudaStre
 int skd_conv2d_fwd_sm100_ex(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
                             const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, int out_h, int out_w,
                             const float* scale, const float* shift, const float* residual, int ldr, int act, float slope, cudaStream_t);
+/* the same convolution with split-K when it has too few output tiles to fill the GPU (the discriminator's 4x4/s2 convolutions on
+   4x8 .. 16x32 maps: K up to 4096 on 2..8 tiles): work units are (tile, K range), raw partial tiles go to `workspace`
+   (skd_conv2d_fwd_sm100_splitk_workspace_floats; 0 = no split, then identical to _ex) and one pass adds them in fixed order and
+   applies scale / shift / residual / act */
+long long skd_conv2d_fwd_sm100_splitk_workspace_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                                       int out_h, int out_w);
+int skd_conv2d_fwd_sm100_splitk(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                                const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, int out_h, int out_w,
+                                const float* scale, const float* shift, const float* residual, int ldr, int act, float slope,
+                                float* workspace, long long workspace_floats, cudaStream_t);
+
+/* 3x3 / stride 1 / pad 1 convolution for Cin, Cout <= 128 (Cin a multiple of 32): the input halo tile of a 16 x 8 pixel output tile is
+   loaded once per 32-channel chunk and the nine taps read it through shifted shared-memory descriptors -- the general kernel moves
+   every activation line L2 -> shared memory nine times and is L2-bound at these widths.  skd_conv2d_fwd_sm100 / _3xtf32 / _ex route
+   eligible shapes here by themselves (skd_set_conv_halo(0) turns that off); this entry calls it directly.  x_lo / w_lo as in _ex. */
+void skd_set_conv_halo(int on);
+int skd_conv3x3_halo_sm100(int N, int H, int W, int Cin, int Cout, const float* x, const float* x_lo, int ldx, const float* w,
+                           const float* w_lo, float* y, int ldy, const float* scale, const float* shift, int act, float slope, cudaStream_t);
 
 /* same kernel, output written through explicit element strides y[n*y_img + oy*y_row + ox*y_pix + c] (every-other-pixel sub-grids:
    the data gradient of a stride-2 convolution is 4 stride-1 convolutions of dy, one per input-pixel parity class) */
@@ -197,6 +215,15 @@ int skd_sgd_step(long long n, float* param, const float* grad, float* momentum_b
    1/sigma (per-channel epilogue scale of the convolution: conv(x, w_bar/sigma) = conv(x, w_bar)/sigma).  One cluster of 8 CTAs. */
 int skd_sn_power_iter(int Cout, int taps, int Cin, const float* w_bar, float* u, float* v, float* u_save, float* v_save, float* sigma,
                       float* inv_sigma_vec, int vec_len, cudaStream_t);
+/* The same iteration for several layers in one call (the discriminator's four spectral-norm layers per forward), each phase a
+   grid over all layers and the whole GPU (the single-layer entry keeps a layer on one 8-CTA cluster: 197 us for l4's 512 x 4096
+   matrix; this one ~10 us for all four).  Deterministic (fixed-order partial sums, no atomics).  `layers` is a HOST array. */
+typedef struct skd_sn_layer {
+  int Cout, taps, Cin, vec_len;
+  const float* w_bar; float* u; float* v; float* u_save; float* v_save; float* sigma; float* inv_sigma_vec;
+} skd_sn_layer;
+long long skd_sn_power_iter_batched_workspace_floats(int n_layers, const skd_sn_layer* layers);
+int skd_sn_power_iter_batched(int n_layers, const skd_sn_layer* layers, float* workspace, cudaStream_t);
 /* d_w (+)= d_wn/sigma - <d_wn, w_bar>/sigma^2 * u v^T : gradient through w_bar/sigma with u, v constant (spectral.py:34-35).
    d_wn is [Cout][taps][Cin_p] (channel-padded wgrad output), d_w / w_bar [Cout][taps][Cin]. */
 long long skd_sn_weight_grad_workspace_doubles(void);      /* zero-initialised once by the caller; self-resetting */
@@ -232,6 +259,7 @@ int skd_bn2d_param_grad(int C, long long P, const float* rstd, const float* sums
                         float* dbeta, int accumulate, cudaStream_t);
 /* Self_Attn core (sagan_models.py:31-40): A = softmax(Q K^T) (no 1/sqrt(d)), O = A V, y = gamma O + x.
    qkv [B*n][ldq] = [q(d) | k(d) | v(C)] (the three 1x1 convolutions as one GEMM), x / o / y [B*n][C], attn [B][n][n]; n <= 128, d <= 64 */
+void skd_set_attn_tensor_cores(int on);   /* 1 (default): the attention products on mma.sync TF32 in split precision; 0: SIMT fp32 (cross-check) */
 int skd_attn_fwd(int B, int n, int C, int d, const float* qkv, int ldq, const float* x, const float* gamma, float* attn, float* o, float* y,
                  float* y_lo, cudaStream_t);
 /* forward-mode tangent along (tqkv, tx): dattn = Adot, to = Odot, ty = gamma Odot + tx */

@@ -61,6 +61,8 @@ struct ConvArgs {
   int reverse;                     // walk the tile list back to front (alternated per layer so a layer starts on the
                                    // activations its producer wrote last, which are still in L2)
   int im2col, rOH, rOW;            // im2col mode: M tiles are 128 consecutive output pixels of the real (rOH x rOW) maps
+  int splits, k_per_split;         // split-K (few tiles, long K: the discriminator's 4x4 convolutions on 4x8 .. 16x32 maps): unit = (tile, K range),
+  long long split_stride;          //   raw fp32 partials go to y + split * split_stride; splitk_epilogue_kernel adds them and applies the epilogue
 };
 
 // PAIR = 1: one CTA per 128 x BLOCK_N tile (cta_group::1).
@@ -127,7 +129,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 
   // pair mode: a tile is two consecutive M tiles (this CTA's is 2*pm + rank; a ragged last one is a phantom that loads zeros)
   const int m_units = (PAIR == 2) ? (a.m_tiles + 1) / 2 : a.m_tiles;
-  const int total_tiles = m_units * a.n_tiles;
+  const int total_tiles = m_units * a.n_tiles * a.splits;       // work units: (tile, K range); the K ranges of a tile are consecutive units
   const int taps = a.KH * a.KW;
   const int k_iters = taps * a.k_chunks;
   // split-precision (passes == 3): a stage holds {x_hi, w_hi, x_lo, w_lo} tiles and every K step issues hi*hi + lo*hi + hi*lo
@@ -141,7 +143,8 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       int stage = 0; uint32_t phase = 0;
       const uint32_t full_bar0 = (PAIR == 2) ? ptx::mapa_shared(&full_bar[0], 0) : 0u;   // the leader's full barriers
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-        const int tl = a.reverse ? total_tiles - 1 - tile : tile;
+        const int tu = a.reverse ? total_tiles - 1 - tile : tile;
+        const int tl = tu / a.splits, sp = tu - tl * a.splits;
         const int mu = tl / a.n_tiles, nt = tl - mu * a.n_tiles;
         const int mt = (PAIR == 2) ? 2 * mu + (int)cta_rank : mu;
         const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
@@ -159,9 +162,11 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         // kc_outer: channel chunk outermost, filter taps innermost -- the taps of one chunk re-read (shifted) the same input lines,
         // L2 hits whatever Cin is.  Taps outermost streams Cin * 128 pixels * 148 CTAs between reuses (310 MB at Cin = 4096, far
         // beyond L2: 679 -> 748 TFLOP/s on the PSP bottleneck) but measured ~5% faster while that working set still fits.
-        const int n_outer = a.kc_outer ? a.k_chunks : taps, n_inner = a.kc_outer ? taps : a.k_chunks;
-        for (int io = 0; io < n_outer; ++io) {
-          for (int ii = 0; ii < n_inner; ++ii) {
+        const int n_inner = a.kc_outer ? taps : a.k_chunks;
+        const int k0 = sp * a.k_per_split, k1 = min(k_iters, k0 + a.k_per_split);
+        {
+          for (int k = k0; k < k1; ++k) {
+            const int io = k / n_inner, ii = k - io * n_inner;
             const int kc = a.kc_outer ? io : ii, tap = a.kc_outer ? ii : io;
             const int kh = tap / a.KW, kw = tap - kh * a.KW;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -211,7 +216,10 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       __syncwarp();
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-      for (int k = 0; k < k_iters; ++k) {
+      const int tu = a.reverse ? total_tiles - 1 - tile : tile;
+      const int sp = tu % a.splits;
+      const int nk = min(k_iters, (sp + 1) * a.k_per_split) - sp * a.k_per_split;      // K steps of this unit (all of them without split-K)
+      for (int k = 0; k < nk; ++k) {
         if (lane == 0) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -233,10 +241,10 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           }
           if constexpr (PAIR == 2) {                          // multicast: the stage / accumulator barriers of both CTAs
             ptx::mma_commit_2cta(&empty_bar[stage]);
-            if (k == k_iters - 1) ptx::mma_commit_2cta(&tmem_full[acc]);
+            if (k == nk - 1) ptx::mma_commit_2cta(&tmem_full[acc]);
           } else {
             ptx::mma_commit(&empty_bar[stage]);               // smem stage reusable once these MMAs retire
-            if (k == k_iters - 1) ptx::mma_commit(&tmem_full[acc]);
+            if (k == nk - 1) ptx::mma_commit(&tmem_full[acc]);
           }
         }
         __syncwarp();
@@ -263,7 +271,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     uint8_t* ring = smem + a.nstages * C::kStageBytes + group * (kResSlots * C::kOutStageBytes);
     uint64_t* rfull = res_full + group * kResSlots;
     auto chunk_valid = [&](int t, int c) -> bool {
-      const int tl_ = a.reverse ? total_tiles - 1 - t : t;
+      const int tl_ = (a.reverse ? total_tiles - 1 - t : t) / a.splits;
       const int nt_ = tl_ % a.n_tiles;
       return c < BLOCK_N / 32 && nt_ * BLOCK_N + c * 32 < a.Cout;
     };
@@ -271,7 +279,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       while (t < total_tiles && !chunk_valid(t, c)) { t += tile_step; c = group; }
     };
     auto issue_residual = [&](int t, int c, int slot) {
-      const int tl_ = a.reverse ? total_tiles - 1 - t : t;
+      const int tl_ = (a.reverse ? total_tiles - 1 - t : t) / a.splits;
       const int mu_ = tl_ / a.n_tiles, nt_ = tl_ - mu_ * a.n_tiles;
       const int mt_ = (PAIR == 2) ? 2 * mu_ + (int)cta_rank : mu_;
       const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
@@ -287,7 +295,8 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     int r_slot = 0; uint32_t r_phase = 0;                            // ring slot / parity of the chunk being consumed
     const uint32_t tmem_empty0 = (PAIR == 2) ? ptx::mapa_shared(&tmem_empty[0], 0) : 0u;   // the leader's tmem_empty barriers
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-      const int tl = a.reverse ? total_tiles - 1 - tile : tile;
+      const int tu = a.reverse ? total_tiles - 1 - tile : tile;
+      const int tl = tu / a.splits, sp = tu - tl * a.splits;
       const int mu = tl / a.n_tiles, nt = tl - mu * a.n_tiles;
       const int mt = (PAIR == 2) ? 2 * mu + (int)cta_rank : mu;
       const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
@@ -295,7 +304,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const int oy = ty * a.BH + dy, ox = tx * a.BW + dx;
       const bool valid = (oy < a.OH) && (ox < a.OW) && (mt < a.m_tiles);
       const size_t pix = ((size_t)img * a.OH + oy) * a.OW + ox;
-      float* yrow = a.y + pix * a.ldy;
+      float* yrow = a.y + (size_t)sp * a.split_stride + pix * a.ldy;
       const float* rrow = (a.residual && valid) ? a.residual + pix * a.ldr : nullptr;
 
       // per-channel affine of this N tile -> shared memory (ones / zeros when absent, zeros past Cout)
@@ -544,7 +553,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   }
   if constexpr (PAIR == 2) {
     // one cluster of two CTAs (the two SMs of a TPC) per 256-pixel tile; persistent over at most kNumSMs / 2 pairs
-    int pairs = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    int pairs = ((a.m_tiles + 1) / 2) * a.n_tiles * a.splits;
     if (pairs > kNumSMs / 2) pairs = kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = st;
@@ -555,7 +564,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fwd_sm100_kernel<BLOCK_N, PAIR>, tx, tw, ty, tx2, tw2, tr, a);
     if (e != cudaSuccess) { set_error("skd_conv2d_fwd_sm100(pair launch)", e); return 0; }
   } else {
-    int grid = a.m_tiles * a.n_tiles;
+    int grid = a.m_tiles * a.n_tiles * a.splits;
     if (grid > kNumSMs) grid = kNumSMs;
     conv_fwd_sm100_kernel<BLOCK_N, PAIR><<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, ty, tx2, tw2, tr, a);
   }
@@ -570,10 +579,45 @@ extern "C" void skd_set_conv_tile_order(int mode) { g_tile_order = mode; g_tile_
 extern "C" void skd_set_conv_cta_pairs(int mode) { g_cta_pairs = mode & 3; }
 extern "C" void skd_set_conv_k_order(int mode) { g_k_order = mode; }
 
+// ---- split-K for convolutions with few output tiles and a long K loop (the discriminator: 256 .. 4096 output pixels, K up to 4096) ----
+// Without it a 4x8-pixel map at batch 8 is 2 x 2 tiles: 4 of 148 SMs walk 128 K steps each.  Units = tiles x K ranges fill the
+// machine; the raw partial tiles go to a caller-provided workspace and one elementwise pass adds them in fixed order and applies
+// the epilogue (scale / shift / residual / activation).
+static int plan_splits(long long tiles, int k_iters) {
+  if (tiles * 2 > kNumSMs || k_iters < 8) return 1;
+  int splits = (int)((kNumSMs + tiles - 1) / tiles);
+  const int cap = k_iters / 4;                                  // at least 4 K steps per unit
+  if (splits > cap) splits = cap;
+  if (splits < 2) return 1;
+  const int kps = (k_iters + splits - 1) / splits;
+  return (k_iters + kps - 1) / kps;                              // no empty range
+}
+
+__global__ void __launch_bounds__(256)
+splitk_epilogue_kernel(const float* __restrict__ ws, long long plane, int splits, long long P, int C4, int ldw4, float* __restrict__ y, int ldy4,
+                       const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ residual, int ldr4,
+                       int act, float slope) {
+  const long long total = P * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C4; const int c4 = (int)(i - p * C4);
+    const float4* src = reinterpret_cast<const float4*>(ws) + p * ldw4 + c4;
+    float4 v = src[0];
+    for (int s2 = 1; s2 < splits; ++s2) {
+      const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (long long)s2 * plane);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (scale) { const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4); v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w; }
+    if (shift) { const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4); v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w; }
+    if (residual) { const float4 r = __ldg(reinterpret_cast<const float4*>(residual) + p * ldr4 + c4); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+    v.x = act_fwd(v.x, act, slope); v.y = act_fwd(v.y, act, slope); v.z = act_fwd(v.z, act, slope); v.w = act_fwd(v.w, act, slope);
+    reinterpret_cast<float4*>(y)[p * ldy4 + c4] = v;
+  }
+}
+
 static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                          const float* x, const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, long long y_row, long long y_img, int oh_req,
                          int ow_req, double* sumsq, int no_store, const float* scale, const float* shift, const float* residual, int ldr, int act, float slope,
-                         int round_tf32, cudaStream_t st) {
+                         int round_tf32, cudaStream_t st, float* split_ws = nullptr, long long split_ws_floats = 0) {
   const char* who = "skd_conv2d_fwd_sm100";
   if (Cin % 4 || ldx % 4 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
     set_error_msg(who, "Cin and the input pitch must be multiples of 4 floats and pointers 16-byte aligned (TMA)");
@@ -583,6 +627,12 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   const int OH = oh_req > 0 ? oh_req : (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
   const int OW = ow_req > 0 ? ow_req : (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
   if (OH <= 0 || OW <= 0 || N <= 0) return 1;
+  // small channel counts, 3x3 / stride 1 / pad 1, dense output, no residual: one halo tile per channel chunk feeds all nine taps
+  // (conv_halo_sm100.cu) instead of nine L2 -> shared-memory passes over the activations
+  if (KH == 3 && KW == 3 && stride == 1 && pad == 1 && dil == 1 && !residual && !sumsq && !no_store && oh_req <= 0 && ow_req <= 0 &&
+      y_row == (long long)OW * ldy && y_img == (long long)OH * OW * ldy && (x_lo == nullptr) == (w_lo == nullptr) &&
+      conv3x3_halo_supported(Cin, Cout, (x_lo && w_lo) ? 3 : 1))
+    return conv3x3_halo_launch(N, H, W, Cin, Cout, x, x_lo, ldx, w, w_lo, y, ldy, scale, shift, act, slope, round_tf32, st);
   ConvArgs a;
   a.Cout = Cout; a.Cin = Cin; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.dil = dil;
   a.rOH = OH; a.rOW = OW; a.im2col = 0;
@@ -622,7 +672,22 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   const bool pair_ok = bn >= 64 && a.m_tiles >= 2;
   const bool kc_outer = (g_k_order == 2) || (g_k_order == 0 && KH * KW > 1 && Cin >= 2048);
   const bool auto_pair = bn == 256 && !kc_outer && (!residual || Cin * KH * KW >= 512);
-  const bool pair = pair_ok && ((g_cta_pairs & 2) ? true : (g_cta_pairs & 1) ? auto_pair : false);
+  bool pair = pair_ok && ((g_cta_pairs & 2) ? true : (g_cta_pairs & 1) ? auto_pair : false);
+  // split-K: flat / im2col tile modes only, channel counts and pitches that are whole float4s, a workspace from the caller
+  a.splits = 1; a.k_per_split = KH * KW * a.k_chunks; a.split_stride = 0;
+  const int ldw = (Cout + 3) / 4 * 4;
+  int splits = 1;
+  if (split_ws && (flat || a.im2col) && !sumsq && !no_store && Cout % 4 == 0 && ldy % 4 == 0 && !(reinterpret_cast<uintptr_t>(y) & 15) &&
+      !((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) &&
+      (!residual || (ldr % 4 == 0 && !(reinterpret_cast<uintptr_t>(residual) & 15))))
+    splits = plan_splits((long long)a.m_tiles * a.n_tiles, KH * KW * a.k_chunks);
+  if (splits > 1 && (long long)splits * P * ldw > split_ws_floats) splits = 1;
+  if (splits > 1) {
+    pair = false;
+    a.splits = splits; a.k_per_split = (KH * KW * a.k_chunks + splits - 1) / splits; a.split_stride = P * ldw;
+    a.y = split_ws; a.ldy = ldw; a.scale = nullptr; a.shift = nullptr; a.residual = nullptr; a.ldr = 0; a.act = 0; a.round_out = 0;
+    a.vec_ok = 1;
+  }
 
   CUtensorMap tx, tw, tx2, tw2;
   auto encode_x = [&](CUtensorMap* m, const float* ptr) -> bool {
@@ -664,6 +729,7 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
   a.reverse = (g_tile_order == 2) ? (g_tile_flip ^= 1) : g_tile_order;
   a.nstages = 0; a.res_prefetch = 0; a.sumsq = sumsq; a.no_store = no_store;
   a.tma_store = !no_store && (ldy % 4 == 0) && !(reinterpret_cast<uintptr_t>(y) & 15) && (y_row % 4 == 0) && (y_img % 4 == 0);
+  if (a.splits > 1) a.tma_store = 0;                            // partial tiles: plain row stores into the workspace planes
   if (strided_out && (!a.tma_store || residual)) { set_error_msg(who, "strided output needs 16-byte aligned strides and no residual"); return 0; }
   if (a.tma_store) {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)a.N};
@@ -686,12 +752,19 @@ static int conv_fwd_impl(int N, int H, int W, int Cin, int Cout, int KH, int KW,
     if (bn == 128) return launch<128, 2>(tx, tw, ty, tx2, tw2, tr, a, st);
     return launch<64, 2>(tx, tw, ty, tx2, tw2, tr, a, st);
   }
+  int ok;
   switch (bn) {
-    case 256: return launch<256, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
-    case 128: return launch<128, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
-    case 64: return launch<64, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
-    default: return launch<32, 1>(tx, tw, ty, tx2, tw2, tr, a, st);
+    case 256: ok = launch<256, 1>(tx, tw, ty, tx2, tw2, tr, a, st); break;
+    case 128: ok = launch<128, 1>(tx, tw, ty, tx2, tw2, tr, a, st); break;
+    case 64: ok = launch<64, 1>(tx, tw, ty, tx2, tw2, tr, a, st); break;
+    default: ok = launch<32, 1>(tx, tw, ty, tx2, tw2, tr, a, st); break;
   }
+  if (!ok || a.splits == 1) return ok;
+  const long long tot4 = P * (Cout / 4);
+  long long blocks = (tot4 + 255) / 256; if (blocks > kNumSMs * 8) blocks = kNumSMs * 8; if (blocks < 1) blocks = 1;
+  splitk_epilogue_kernel<<<(int)blocks, 256, 0, st>>>(split_ws, a.split_stride, a.splits, P, Cout / 4, ldw / 4, y, ldy / 4, scale, shift, residual,
+                                                     ldr / 4, act, slope);
+  return finish("skd_conv2d_fwd_sm100(split-K epilogue)");
 }
 
 extern "C" int skd_conv2d_fwd_sm100(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
@@ -742,4 +815,29 @@ extern "C" int skd_conv2d_fwd_sm100_ex(int N, int H, int W, int Cin, int Cout, i
   if ((x_lo == nullptr) != (w_lo == nullptr)) { set_error_msg("skd_conv2d_fwd_sm100_ex", "x_lo and w_lo must be given together"); return 0; }
   return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, x_lo, ldx, w, w_lo, y, ldy, (long long)OW * ldy, (long long)OH * OW * ldy,
                        out_h, out_w, nullptr, 0, scale, shift, residual, ldr, act, slope, 0, st);
+}
+
+// The same convolution with split-K where the tile count is small (plan_splits): `workspace` holds the partial planes.
+extern "C" long long skd_conv2d_fwd_sm100_splitk_workspace_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                                                                 int dil, int out_h, int out_w) {
+  const int OH = out_h > 0 ? out_h : (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+  const int OW = out_w > 0 ? out_w : (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+  if (OH <= 0 || OW <= 0 || N <= 0 || Cout % 4) return 0;
+  const long long P = (long long)N * OH * OW;
+  const int bn = Cout > 128 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
+  const long long tiles = ((P + kBlockM - 1) / kBlockM) * ((Cout + bn - 1) / bn);
+  const int splits = plan_splits(tiles, KH * KW * ((Cin + kBlockK - 1) / kBlockK));
+  return splits > 1 ? (long long)splits * P * Cout : 0;
+}
+
+extern "C" int skd_conv2d_fwd_sm100_splitk(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
+                                           const float* x_lo, int ldx, const float* w, const float* w_lo, float* y, int ldy, int out_h, int out_w,
+                                           const float* scale, const float* shift, const float* residual, int ldr, int act, float slope,
+                                           float* workspace, long long workspace_floats, cudaStream_t st) {
+  const int OH = out_h > 0 ? out_h : (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+  const int OW = out_w > 0 ? out_w : (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+  if ((x_lo == nullptr) != (w_lo == nullptr)) { set_error_msg("skd_conv2d_fwd_sm100_splitk", "x_lo and w_lo must be given together"); return 0; }
+  if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 15)) { set_error_msg("skd_conv2d_fwd_sm100_splitk", "workspace not 16-byte aligned"); return 0; }
+  return conv_fwd_impl(N, H, W, Cin, Cout, KH, KW, stride, pad, dil, x, x_lo, ldx, w, w_lo, y, ldy, (long long)OW * ldy, (long long)OH * OW * ldy,
+                       out_h, out_w, nullptr, 0, scale, shift, residual, ldr, act, slope, 0, st, workspace, workspace_floats);
 }

@@ -79,6 +79,67 @@ __device__ __forceinline__ void block_gemm(int M, int N, int K, FA a, FB b, FS s
   }
 }
 
+// The same product on the tensor cores: mma.sync m16n8k8 TF32 in split precision (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32-grade like
+// the 3xTF32 convolutions), operands through the same shared-memory accessors.  Warp tiles of 16 x 8*NT, eight warps round-robin.
+// The attention products are 32..128 positions wide (n x n x d scores, n x C x n values): far below one tcgen05 tile pipeline's
+// start-up cost, so the warp-level MMA is the tensor-core path that fits them.
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int NT, class FA, class FB, class FS>
+__device__ __forceinline__ void block_gemm_tc(int M, int N, int K, FA a, FB b, FS store) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = (M + 15) / 16, nt = (N + 8 * NT - 1) / (8 * NT);
+  for (int tile = warp; tile < mt * nt; tile += nw) {
+    const int m0 = (tile / nt) * 16, n0 = (tile % nt) * 8 * NT;
+    const int r0 = min(m0 + g, M - 1), r1 = min(m0 + g + 8, M - 1);
+    int cn[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) cn[j] = min(n0 + 8 * j + g, N - 1);
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      const bool va = k0 + t < K, vb = k0 + t + 4 < K;
+      const int ka = min(k0 + t, K - 1), kb = min(k0 + t + 4, K - 1);
+      float af[4];
+      af[0] = va ? a(r0, ka) : 0.f; af[1] = va ? a(r1, ka) : 0.f; af[2] = vb ? a(r0, kb) : 0.f; af[3] = vb ? a(r1, kb) : 0.f;
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float h = ptx::round_tf32(af[q]); ah[q] = __float_as_uint(h); al[q] = __float_as_uint(ptx::round_tf32(af[q] - h)); }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float b0 = va ? b(ka, cn[j]) : 0.f, b1 = vb ? b(kb, cn[j]) : 0.f;
+        const float h0 = ptx::round_tf32(b0), h1 = ptx::round_tf32(b1);
+        const uint32_t bh[2] = {__float_as_uint(h0), __float_as_uint(h1)};
+        const uint32_t bl[2] = {__float_as_uint(ptx::round_tf32(b0 - h0)), __float_as_uint(ptx::round_tf32(b1 - h1))};
+        mma_m16n8k8_tf32(acc[j], al, bh);
+        mma_m16n8k8_tf32(acc[j], ah, bl);
+        mma_m16n8k8_tf32(acc[j], ah, bh);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int col = n0 + 8 * j + 2 * t;
+      if (m0 + g < M) { if (col < N) store(m0 + g, col, acc[j][0]); if (col + 1 < N) store(m0 + g, col + 1, acc[j][1]); }
+      if (m0 + g + 8 < M) { if (col < N) store(m0 + g + 8, col, acc[j][2]); if (col + 1 < N) store(m0 + g + 8, col + 1, acc[j][3]); }
+    }
+  }
+}
+
+// tc != 0: tensor cores (mma.sync, split precision); 0: the SIMT fp32 product (kept as the cross-check; skd_set_attn_tensor_cores)
+template <int TM, int TN, class FA, class FB, class FS>
+__device__ __forceinline__ void attn_gemm(int tc, int M, int N, int K, FA a, FB b, FS store) {
+  if (tc) block_gemm_tc<4>(M, N, K, a, b, store);
+  else block_gemm<TM, TN>(M, N, K, a, b, store);
+}
+
+int g_attn_tc = 1;
+
 // ====================================================================================================================
 // Spectral normalisation (networks/spectral.py:23-35)
 // ====================================================================================================================
@@ -157,7 +218,106 @@ sn_power_iter_kernel(int Cout, int taps, int Cin, const float* __restrict__ w, f
   }
 }
 
-constexpr int kDotBlocks = 64;
+// ---- the same iteration for SEVERAL layers at once, spread over the whole GPU (the discriminator's four layers per forward) ----
+// The cluster kernel above keeps one layer on 8 SMs: 197 us for the 512 x 4096 matrix of l4 (two passes over 8 MB through 8 SMs).
+// Here every phase is a grid over all layers: (1) partial W^T u per 32-row block, (2) v = normalize(sum of partials) [fixed order],
+// (3) s = W v, one warp per row, (4) u = normalize(s), sigma = u . s.  Deterministic (no atomics): replicas of a data-parallel
+// job keep bit-identical u, v.
+constexpr int kSnBatchMax = 8, kSnRowBlock = 32, kSnKBlock = 1024;
+struct SnLayer {
+  int Cout, taps, Cin, K, vec_len, n_rb, n_kb, blk1, blk3;     // blk1 / blk3: first block of this layer in phase 1 / 3
+  const float* w; float *u, *v, *u_save, *v_save, *sigma, *inv_vec;
+  float *tpart, *vlin, *s;                                      // workspace: [n_rb][K], [K], [Cout]
+};
+struct SnBatch { int n; SnLayer L[kSnBatchMax]; };
+
+__device__ __forceinline__ int sn_find_layer(const SnBatch& b, int blk, bool phase3) {
+  int l = 0;
+  for (int i = 1; i < b.n; ++i) if (blk >= (phase3 ? b.L[i].blk3 : b.L[i].blk1)) l = i;
+  return l;
+}
+
+__global__ void __launch_bounds__(256)
+sn_phase1_kernel(const __grid_constant__ SnBatch b) {
+  __shared__ float su[kSnRowBlock];
+  const int li = sn_find_layer(b, blockIdx.x, false);
+  const SnLayer& L = b.L[li];
+  const int rel = blockIdx.x - L.blk1, rb = rel / L.n_kb, kb = rel - rb * L.n_kb;
+  const int r0 = rb * kSnRowBlock, r1 = min(L.Cout, r0 + kSnRowBlock);
+  if (threadIdx.x < r1 - r0) su[threadIdx.x] = L.u[r0 + threadIdx.x];
+  __syncthreads();
+  const int k0 = kb * kSnKBlock + threadIdx.x;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* wp = L.w + (size_t)r0 * L.K;
+  for (int r = 0; r < r1 - r0; ++r, wp += L.K) {
+    const float ur = su[r];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int k = k0 + j * 256; if (k < L.K) acc[j] = fmaf(__ldg(wp + k), ur, acc[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const int k = k0 + j * 256; if (k < L.K) L.tpart[(size_t)rb * L.K + k] = acc[j]; }
+}
+
+__global__ void __launch_bounds__(1024)
+sn_phase2_kernel(const __grid_constant__ SnBatch b) {
+  __shared__ float s_t[kSnMaxK];
+  __shared__ float s_red[64];
+  const SnLayer& L = b.L[blockIdx.x];
+  float n2 = 0.f;
+  for (int k = threadIdx.x; k < L.K; k += 1024) {
+    float tot = 0.f;
+    for (int rb = 0; rb < L.n_rb; ++rb) tot += L.tpart[(size_t)rb * L.K + k];
+    s_t[k] = tot; n2 = fmaf(tot, tot, n2);
+  }
+  n2 = block_sum(n2, s_red);
+  const float inv_t = 1.f / (sqrtf(n2) + 1e-12f);   // l2normalize: v / (|v| + eps), spectral.py:10-11
+  for (int k = threadIdx.x; k < L.K; k += 1024) {
+    const float vv = s_t[k] * inv_t;
+    L.vlin[k] = vv;
+    const int kr = (k % L.Cin) * L.taps + k / L.Cin;            // the reference's flattening of (Cout, Cin, KH, KW).view(Cout, -1)
+    L.v[kr] = vv;
+    if (L.v_save) L.v_save[kr] = vv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sn_phase3_kernel(const __grid_constant__ SnBatch b) {
+  const int li = sn_find_layer(b, blockIdx.x, true);
+  const SnLayer& L = b.L[li];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = (blockIdx.x - L.blk3) * 8 + warp;
+  if (r >= L.Cout) return;
+  const float* wp = L.w + (size_t)r * L.K;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = lane;
+  for (; k + 96 < L.K; k += 128) {
+    a0 = fmaf(__ldg(wp + k), L.vlin[k], a0); a1 = fmaf(__ldg(wp + k + 32), L.vlin[k + 32], a1);
+    a2 = fmaf(__ldg(wp + k + 64), L.vlin[k + 64], a2); a3 = fmaf(__ldg(wp + k + 96), L.vlin[k + 96], a3);
+  }
+  for (; k < L.K; k += 32) a0 = fmaf(__ldg(wp + k), L.vlin[k], a0);
+  const float acc = warp_sum((a0 + a1) + (a2 + a3));
+  if (lane == 0) L.s[r] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+sn_phase4_kernel(const __grid_constant__ SnBatch b) {
+  __shared__ float s_red[64];
+  const SnLayer& L = b.L[blockIdx.x];
+  float q = 0.f;
+  for (int i = threadIdx.x; i < L.Cout; i += 256) { const float sv = L.s[i]; q = fmaf(sv, sv, q); }
+  const float tot = block_sum(q, s_red);
+  const float inv_s = 1.f / (sqrtf(tot) + 1e-12f);
+  for (int i = threadIdx.x; i < L.Cout; i += 256) {
+    const float uu = L.s[i] * inv_s;
+    L.u[i] = uu;
+    if (L.u_save) L.u_save[i] = uu;
+  }
+  const float sg = tot * inv_s;                     // u . (W v) = |Wv|^2 / (|Wv| + eps)
+  if (threadIdx.x == 0) L.sigma[0] = sg;
+  for (int i = threadIdx.x; i < L.vec_len; i += 256) L.inv_vec[i] = 1.f / sg;
+}
+
+constexpr int kDotBlocks = 296;
 // <dWn, W> over the valid (un-padded) entries; deterministic: fixed per-block partials, the last block adds them in order
 __global__ void __launch_bounds__(256)
 sn_grad_dot_kernel(int Cout, int taps, int Cin, int Cin_p, const float* __restrict__ dwn, const float* __restrict__ w, double* ws) {
@@ -165,9 +325,17 @@ sn_grad_dot_kernel(int Cout, int taps, int Cin, int Cin_p, const float* __restri
   __shared__ bool last;
   const long long total = (long long)Cout * taps * Cin;
   double acc = 0.0;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int ci = (int)(i % Cin); const long long rt = i / Cin;
-    acc += (double)__ldg(dwn + rt * Cin_p + ci) * (double)__ldg(w + i);
+  const long long step = (long long)gridDim.x * 256;
+  for (long long i0 = (long long)blockIdx.x * 256 + threadIdx.x; i0 < total; i0 += 4 * step) {
+    float a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = i0 + j * step;
+      const bool ok = i < total;
+      const int ci = ok ? (int)(i % Cin) : 0; const long long rt = ok ? i / Cin : 0;
+      a[j] = ok ? __ldg(dwn + rt * Cin_p + ci) : 0.f; b[j] = ok ? __ldg(w + i) : 0.f;
+    }
+    acc += ((double)a[0] * (double)b[0] + (double)a[1] * (double)b[1]) + ((double)a[2] * (double)b[2] + (double)a[3] * (double)b[3]);
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -239,7 +407,7 @@ dgrad_weight_prep_kernel(int Cout, int Cin, int Cin_p, const float* __restrict__
 // ====================================================================================================================
 // BatchNorm2d with batch statistics on <= 32 channels (nn.BatchNorm2d(19), sagan_models.py:147)
 // ====================================================================================================================
-constexpr int kBnBlocks = 128;
+constexpr int kBnBlocks = 296;
 
 // per-channel sums over pixels of up to three products; lane = channel, warp = pixel.
 //   MODE 0: S1 = sum x,      S2 = sum x^2                                  (x strided)                 -> statistics
@@ -258,14 +426,24 @@ bn2d_reduce_kernel(int N, int C, int HW, const float* __restrict__ x, long long 
   double s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (lane < C) {
     const float m = MODE ? mean[lane] : 0.f, r = MODE ? rstd[lane] : 0.f;
-    for (long long p = (long long)blockIdx.x * 8 + warp; p < P; p += (long long)gridDim.x * 8) {
-      const long long n = p / HW, q = p - n * HW;
-      const float xv = __ldg(x + n * sn + lane * sc + q * sp);
-      if (MODE == 0) { s1 += xv; s2 += (double)xv * xv; }
-      else {
-        const float av = __ldg(a + p * ld + lane);
-        s1 += av; s2 += (double)(av * ((xv - m) * r));
-        if (b2) s3 += (double)(av * __ldg(b2 + p * ld + lane));
+    // four pixels per iteration: 4-12 independent loads in flight per lane (one pixel per iteration was latency-bound: 50 us for 67 080 pixels)
+    const long long step = (long long)gridDim.x * 8;
+    for (long long p0 = (long long)blockIdx.x * 8 + warp; p0 < P; p0 += 4 * step) {
+      float xv[4], av[4], bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long p = p0 + j * step;
+        const bool ok = p < P;
+        const long long n = ok ? p / HW : 0, q = ok ? p - n * HW : 0;
+        xv[j] = ok ? __ldg(x + n * sn + lane * sc + q * sp) : 0.f;
+        av[j] = (MODE && ok) ? __ldg(a + p * ld + lane) : 0.f;
+        bv[j] = (MODE && ok && b2) ? __ldg(b2 + p * ld + lane) : 0.f;
+        if (MODE && !ok) xv[j] = m;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (MODE == 0) { s1 += xv[j]; s2 += (double)xv[j] * xv[j]; }
+        else { s1 += av[j]; s2 += (double)(av[j] * ((xv[j] - m) * r)); s3 += (double)(av[j] * bv[j]); }
       }
     }
   }
@@ -553,7 +731,7 @@ __device__ __forceinline__ void softmax_rows(float* s, int n, int ld) {
 // grid (B, C / 64).  Every slice CTA recomputes the n x n scores (n^2 d MACs, less than its n^2 64 share of A V).
 __global__ void __launch_bounds__(256)
 attn_fwd_kernel(int n, int C, int d, const float* __restrict__ qkv, int ldq, const float* __restrict__ x, const float* __restrict__ gamma,
-                float* __restrict__ attn, float* __restrict__ o, float* __restrict__ y, float* __restrict__ y_lo) {
+                float* __restrict__ attn, float* __restrict__ o, float* __restrict__ y, float* __restrict__ y_lo, int tc) {
   extern __shared__ float smem[];
   const int b = blockIdx.x, sl = blockIdx.y;
   const int ldA = n + 1, ldD = d + 1, CS = kAttnFwdSlice;
@@ -567,7 +745,7 @@ attn_fwd_kernel(int n, int C, int d, const float* __restrict__ qkv, int ldq, con
   const int c0 = sl * CS, cw = min(CS, C - c0);
   load_rows(sV, CS + 1, base + 2 * d + c0, ldq, n, cw);
   __syncthreads();
-  block_gemm<4, 4>(n, n, d, [&](int i, int k) { return sQ[i * ldD + k]; }, [&](int k, int j) { return sK[j * ldD + k]; },
+  attn_gemm<4, 4>(tc, n, n, d, [&](int i, int k) { return sQ[i * ldD + k]; }, [&](int k, int j) { return sK[j * ldD + k]; },
                    [&](int i, int j, float v) { sA[i * ldA + j] = v; });
   __syncthreads();
   softmax_rows(sA, n, ldA);
@@ -575,7 +753,7 @@ attn_fwd_kernel(int n, int C, int d, const float* __restrict__ qkv, int ldq, con
   if (sl == 0 && attn)
     for (int i = threadIdx.x; i < n * n; i += 256) attn[(size_t)b * n * n + i] = sA[(i / n) * ldA + (i % n)];
   const float gm = gamma[0];
-  block_gemm<4, 4>(n, cw, n, [&](int i, int k) { return sA[i * ldA + k]; }, [&](int k, int j) { return sV[k * (CS + 1) + j]; },
+  attn_gemm<4, 4>(tc, n, cw, n, [&](int i, int k) { return sA[i * ldA + k]; }, [&](int k, int j) { return sV[k * (CS + 1) + j]; },
                    [&](int i, int j, float v) {
                      const size_t idx = ((size_t)b * n + i) * C + c0 + j;
                      if (o) o[idx] = v;
@@ -589,7 +767,7 @@ attn_fwd_kernel(int n, int C, int d, const float* __restrict__ qkv, int ldq, con
 __global__ void __launch_bounds__(256)
 attn_tangent_kernel(int n, int C, int d, const float* __restrict__ qkv, const float* __restrict__ tqkv, int ldq,
                     const float* __restrict__ attn, const float* __restrict__ tx, const float* __restrict__ gamma, float* __restrict__ dattn,
-                    float* __restrict__ to, float* __restrict__ ty, float* __restrict__ ty_lo) {
+                    float* __restrict__ to, float* __restrict__ ty, float* __restrict__ ty_lo, int tc) {
   extern __shared__ float smem[];
   const int b = blockIdx.x, sl = blockIdx.y;
   const int ldA = n + 1, ldD = d + 1, CS = kAttnFwdSlice, ldV = CS + 1;
@@ -607,7 +785,7 @@ attn_tangent_kernel(int n, int C, int d, const float* __restrict__ qkv, const fl
   load_rows(sTQ, ldD, tbase, ldq, n, d);
   load_rows(sTK, ldD, tbase + d, ldq, n, d);
   __syncthreads();
-  block_gemm<4, 4>(n, n, 2 * d,
+  attn_gemm<4, 4>(tc, n, n, 2 * d,
                    [&](int i, int k) { return k < d ? sTQ[i * ldD + k] : sQ[i * ldD + k - d]; },
                    [&](int k, int j) { return k < d ? sK[j * ldD + k] : sTK[j * ldD + k - d]; },
                    [&](int i, int j, float v) { sdA[i * ldA + j] = v; });
@@ -631,7 +809,7 @@ attn_tangent_kernel(int n, int C, int d, const float* __restrict__ qkv, const fl
   load_rows(sTV, ldV, tbase + 2 * d + c0, ldq, n, cw);
   __syncthreads();
   const float gm = gamma[0];
-  block_gemm<4, 4>(n, cw, 2 * n,
+  attn_gemm<4, 4>(tc, n, cw, 2 * n,
                    [&](int i, int k) { return k < n ? sdA[i * ldA + k] : sA[i * ldA + k - n]; },
                    [&](int k, int j) { return k < n ? sV[k * ldV + j] : sTV[(k - n) * ldV + j]; },
                    [&](int i, int j, float v) {
@@ -653,7 +831,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd1_kernel(int n, int C, int d, const float* __restrict__ qkv, const float* __restrict__ tqkv, int ldq, const float* __restrict__ attn,
                  const float* __restrict__ dattn, const float* __restrict__ o, const float* __restrict__ to, const float* __restrict__ gamma,
                  const float* __restrict__ gy, const float* __restrict__ gty, float* __restrict__ gqkv, float* __restrict__ gtqkv,
-                 float* __restrict__ ws, float* __restrict__ gpart) {
+                 float* __restrict__ ws, float* __restrict__ gpart, int tc) {
   extern __shared__ float smem[];
   __shared__ float red[64];
   const int b = blockIdx.x, sl = blockIdx.y, nsl = gridDim.y;
@@ -686,21 +864,21 @@ attn_bwd1_kernel(int n, int C, int d, const float* __restrict__ qkv, const float
   if (threadIdx.x == 0) gpart[b * nsl + sl] = gp;
   __syncthreads();
   // gV[j][c] = sum_i A[i][j] Go[i][c] (+ Adot[i][j] Gto[i][c])
-  block_gemm<4, 2>(n, cw, DUAL ? 2 * n : n,
+  attn_gemm<4, 2>(tc, n, cw, DUAL ? 2 * n : n,
                    [&](int j, int k) { return (!DUAL || k < n) ? sA[k * ldA + j] : sdA[(k - n) * ldA + j]; },
                    [&](int k, int c) { return (!DUAL || k < n) ? sGO[k * ldV + c] : sGTO[(k - n) * ldV + c]; },
                    [&](int j, int c, float v) { gqkv[(row0 + j) * ldq + 2 * d + c0 + c] = v; });
   if (DUAL)
-    block_gemm<4, 2>(n, cw, n, [&](int j, int k) { return sA[k * ldA + j]; }, [&](int k, int c) { return sGTO[k * ldV + c]; },
+    attn_gemm<4, 2>(tc, n, cw, n, [&](int j, int k) { return sA[k * ldA + j]; }, [&](int k, int c) { return sGTO[k * ldV + c]; },
                      [&](int j, int c, float v) { gtqkv[(row0 + j) * ldq + 2 * d + c0 + c] = v; });
   float* w1 = ws + (((size_t)b * nsl + sl) * 2) * n * n;
   // Abar1[i][j] = sum_c Go[i][c] V[j][c] (+ Gto[i][c] Vdot[j][c])
-  block_gemm<4, 4>(n, n, DUAL ? 2 * cw : cw,
+  attn_gemm<4, 4>(tc, n, n, DUAL ? 2 * cw : cw,
                    [&](int i, int k) { return (!DUAL || k < cw) ? sGO[i * ldV + k] : sGTO[i * ldV + k - cw]; },
                    [&](int k, int j) { return (!DUAL || k < cw) ? sV[j * ldV + k] : sTV[j * ldV + k - cw]; },
                    [&](int i, int j, float v) { w1[i * n + j] = v; });
   if (DUAL)
-    block_gemm<4, 4>(n, n, cw, [&](int i, int k) { return sGTO[i * ldV + k]; }, [&](int k, int j) { return sV[j * ldV + k]; },
+    attn_gemm<4, 4>(tc, n, n, cw, [&](int i, int k) { return sGTO[i * ldV + k]; }, [&](int k, int j) { return sV[j * ldV + k]; },
                      [&](int i, int j, float v) { w1[(size_t)n * n + i * n + j] = v; });
 }
 
@@ -714,7 +892,7 @@ template <bool DUAL>
 __global__ void __launch_bounds__(256)
 attn_bwd2_kernel(int B, int n, int d, int nsl, const float* __restrict__ qkv, const float* __restrict__ tqkv, int ldq,
                  const float* __restrict__ attn, const float* __restrict__ ws, const float* __restrict__ gpart, float* __restrict__ gqkv,
-                 float* __restrict__ gtqkv, float* ggamma, int accumulate) {
+                 float* __restrict__ gtqkv, float* ggamma, int accumulate, int tc) {
   extern __shared__ float smem[];
   const int b = blockIdx.x;
   const int ldA = n + 1, ldD = d + 1;
@@ -733,7 +911,7 @@ attn_bwd2_kernel(int B, int n, int d, int nsl, const float* __restrict__ qkv, co
   }
   __syncthreads();
   if (DUAL) {
-    block_gemm<4, 4>(n, n, 2 * d,
+    attn_gemm<4, 4>(tc, n, n, 2 * d,
                      [&](int i, int k) { return k < d ? sTQ[i * ldD + k] : sQ[i * ldD + k - d]; },
                      [&](int k, int j) { return k < d ? sK[j * ldD + k] : sTK[j * ldD + k - d]; },
                      [&](int i, int j, float v) { sGT[i * ldA + j] = v; });
@@ -778,18 +956,18 @@ attn_bwd2_kernel(int B, int n, int d, int nsl, const float* __restrict__ qkv, co
     }
   }
   __syncthreads();
-  block_gemm<4, 2>(n, d, DUAL ? 2 * n : n,
+  attn_gemm<4, 2>(tc, n, d, DUAL ? 2 * n : n,
                    [&](int i, int k) { return (!DUAL || k < n) ? sGS[i * ldA + k] : sGT[i * ldA + k - n]; },
                    [&](int k, int c) { return (!DUAL || k < n) ? sK[k * ldD + c] : sTK[(k - n) * ldD + c]; },
                    [&](int i, int c, float v) { gqkv[(row0 + i) * ldq + c] = v; });
-  block_gemm<4, 2>(n, d, DUAL ? 2 * n : n,
+  attn_gemm<4, 2>(tc, n, d, DUAL ? 2 * n : n,
                    [&](int j, int k) { return (!DUAL || k < n) ? sGS[k * ldA + j] : sGT[(k - n) * ldA + j]; },
                    [&](int k, int c) { return (!DUAL || k < n) ? sQ[k * ldD + c] : sTQ[(k - n) * ldD + c]; },
                    [&](int j, int c, float v) { gqkv[(row0 + j) * ldq + d + c] = v; });
   if (DUAL) {
-    block_gemm<4, 2>(n, d, n, [&](int i, int k) { return sGT[i * ldA + k]; }, [&](int k, int c) { return sK[k * ldD + c]; },
+    attn_gemm<4, 2>(tc, n, d, n, [&](int i, int k) { return sGT[i * ldA + k]; }, [&](int k, int c) { return sK[k * ldD + c]; },
                      [&](int i, int c, float v) { gtqkv[(row0 + i) * ldq + c] = v; });
-    block_gemm<4, 2>(n, d, n, [&](int j, int k) { return sGT[k * ldA + j]; }, [&](int k, int c) { return sQ[k * ldD + c]; },
+    attn_gemm<4, 2>(tc, n, d, n, [&](int j, int k) { return sGT[k * ldA + j]; }, [&](int k, int c) { return sQ[k * ldD + c]; },
                      [&](int j, int c, float v) { gtqkv[(row0 + j) * ldq + d + c] = v; });
   }
   if (b == 0 && threadIdx.x == 0 && ggamma) {
@@ -833,6 +1011,43 @@ extern "C" int skd_sn_power_iter(int Cout, int taps, int Cin, const float* w_bar
   cudaError_t e = cudaLaunchKernelEx(&cfg, sn_power_iter_kernel, Cout, taps, Cin, w_bar, u, v, u_save, v_save, sigma, inv_sigma_vec, vec_len);
   if (e != cudaSuccess) { set_error(who, e); return 0; }
   return finish(who);
+}
+
+static long long sn_layer_ws_floats(int Cout, int K) {
+  const long long n_rb = (Cout + kSnRowBlock - 1) / kSnRowBlock;
+  return ((n_rb + 1) * K + Cout + 3) / 4 * 4;
+}
+
+extern "C" long long skd_sn_power_iter_batched_workspace_floats(int n_layers, const skd_sn_layer* layers) {
+  long long t = 0;
+  for (int i = 0; i < n_layers; ++i) t += sn_layer_ws_floats(layers[i].Cout, layers[i].taps * layers[i].Cin);
+  return t;
+}
+
+extern "C" int skd_sn_power_iter_batched(int n_layers, const skd_sn_layer* layers, float* workspace, cudaStream_t st) {
+  const char* who = "skd_sn_power_iter_batched";
+  if (n_layers <= 0) return 1;
+  if (n_layers > kSnBatchMax) { set_error_msg(who, "at most 8 layers per call"); return 0; }
+  SnBatch b; b.n = n_layers;
+  int blk1 = 0, blk3 = 0;
+  float* ws = workspace;
+  for (int i = 0; i < n_layers; ++i) {
+    const skd_sn_layer& in = layers[i];
+    SnLayer& L = b.L[i];
+    L.Cout = in.Cout; L.taps = in.taps; L.Cin = in.Cin; L.K = in.taps * in.Cin; L.vec_len = in.vec_len;
+    if (L.K > kSnMaxK || L.K <= 0 || L.Cout <= 0) { set_error_msg(who, "weight matrix too large (K <= 8192)"); return 0; }
+    L.n_rb = (L.Cout + kSnRowBlock - 1) / kSnRowBlock; L.n_kb = (L.K + kSnKBlock - 1) / kSnKBlock;
+    L.blk1 = blk1; blk1 += L.n_rb * L.n_kb;
+    L.blk3 = blk3; blk3 += (L.Cout + 7) / 8;
+    L.w = in.w_bar; L.u = in.u; L.v = in.v; L.u_save = in.u_save; L.v_save = in.v_save; L.sigma = in.sigma; L.inv_vec = in.inv_sigma_vec;
+    L.tpart = ws; L.vlin = ws + (size_t)L.n_rb * L.K; L.s = L.vlin + L.K;
+    ws += sn_layer_ws_floats(L.Cout, L.K);
+  }
+  sn_phase1_kernel<<<blk1, 256, 0, st>>>(b);
+  sn_phase2_kernel<<<n_layers, 1024, 0, st>>>(b);
+  sn_phase3_kernel<<<blk3, 256, 0, st>>>(b);
+  sn_phase4_kernel<<<n_layers, 256, 0, st>>>(b);
+  return finish(who, 4);
 }
 
 extern "C" long long skd_sn_weight_grad_workspace_doubles(void) { return 1 + kDotBlocks + 1; }
@@ -953,13 +1168,15 @@ extern "C" int skd_gp_direction(int B, long long len, const float* g, const floa
   return finish("skd_gp_direction");
 }
 
+extern "C" void skd_set_attn_tensor_cores(int on) { g_attn_tc = on ? 1 : 0; }
+
 extern "C" int skd_attn_fwd(int B, int n, int C, int d, const float* qkv, int ldq, const float* x, const float* gamma, float* attn, float* o,
                             float* y, float* y_lo, cudaStream_t st) {
   const char* who = "skd_attn_fwd";
   if (!attn_shape_ok(B, n, C, d, ldq, who)) return 0;
   const size_t bytes = ((size_t)n * (n + 1) + 2 * (size_t)n * (d + 1) + (size_t)n * (kAttnFwdSlice + 1)) * 4;
   if (!set_smem(attn_fwd_kernel, bytes, who)) return 0;
-  attn_fwd_kernel<<<dim3(B, (C + kAttnFwdSlice - 1) / kAttnFwdSlice), 256, bytes, st>>>(n, C, d, qkv, ldq, x, gamma, attn, o, y, y_lo);
+  attn_fwd_kernel<<<dim3(B, (C + kAttnFwdSlice - 1) / kAttnFwdSlice), 256, bytes, st>>>(n, C, d, qkv, ldq, x, gamma, attn, o, y, y_lo, g_attn_tc);
   return finish(who);
 }
 
@@ -971,7 +1188,7 @@ extern "C" int skd_attn_tangent_fwd(int B, int n, int C, int d, const float* qkv
   if (region < need) region = need;
   const size_t bytes = (2 * (size_t)n * (n + 1) + region) * 4;
   if (!set_smem(attn_tangent_kernel, bytes, who)) return 0;
-  attn_tangent_kernel<<<dim3(B, (C + kAttnFwdSlice - 1) / kAttnFwdSlice), 256, bytes, st>>>(n, C, d, qkv, tqkv, ldq, attn, tx, gamma, dattn, to, ty, ty_lo);
+  attn_tangent_kernel<<<dim3(B, (C + kAttnFwdSlice - 1) / kAttnFwdSlice), 256, bytes, st>>>(n, C, d, qkv, tqkv, ldq, attn, tx, gamma, dattn, to, ty, ty_lo, g_attn_tc);
   return finish(who);
 }
 
@@ -994,12 +1211,12 @@ extern "C" int skd_attn_bwd(int B, int n, int C, int d, const float* qkv, int ld
   const size_t b2 = ((dual ? 2 : 1) * (size_t)n * (n + 1) + (dual ? 4 : 2) * (size_t)n * (d + 1)) * 4;
   if (dual) {
     if (!set_smem(attn_bwd1_kernel<true>, b1, who) || !set_smem(attn_bwd2_kernel<true>, b2, who)) return 0;
-    attn_bwd1_kernel<true><<<dim3(B, nsl), 256, b1, st>>>(n, C, d, qkv, tqkv, ldq, attn, dattn, o, to, gamma, gy, gty, gqkv, gtqkv, workspace, gpart);
-    attn_bwd2_kernel<true><<<B, 256, b2, st>>>(B, n, d, nsl, qkv, tqkv, ldq, attn, workspace, gpart, gqkv, gtqkv, ggamma, accumulate);
+    attn_bwd1_kernel<true><<<dim3(B, nsl), 256, b1, st>>>(n, C, d, qkv, tqkv, ldq, attn, dattn, o, to, gamma, gy, gty, gqkv, gtqkv, workspace, gpart, g_attn_tc);
+    attn_bwd2_kernel<true><<<B, 256, b2, st>>>(B, n, d, nsl, qkv, tqkv, ldq, attn, workspace, gpart, gqkv, gtqkv, ggamma, accumulate, g_attn_tc);
   } else {
     if (!set_smem(attn_bwd1_kernel<false>, b1, who) || !set_smem(attn_bwd2_kernel<false>, b2, who)) return 0;
-    attn_bwd1_kernel<false><<<dim3(B, nsl), 256, b1, st>>>(n, C, d, qkv, nullptr, ldq, attn, nullptr, o, nullptr, gamma, gy, nullptr, gqkv, nullptr, workspace, gpart);
-    attn_bwd2_kernel<false><<<B, 256, b2, st>>>(B, n, d, nsl, qkv, nullptr, ldq, attn, workspace, gpart, gqkv, nullptr, ggamma, accumulate);
+    attn_bwd1_kernel<false><<<dim3(B, nsl), 256, b1, st>>>(n, C, d, qkv, nullptr, ldq, attn, nullptr, o, nullptr, gamma, gy, nullptr, gqkv, nullptr, workspace, gpart, g_attn_tc);
+    attn_bwd2_kernel<false><<<B, 256, b2, st>>>(B, n, d, nsl, qkv, nullptr, ldq, attn, workspace, gpart, gqkv, nullptr, ggamma, accumulate, g_attn_tc);
   }
   return finish(who, 2);
 }

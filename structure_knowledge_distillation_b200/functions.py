@@ -122,6 +122,27 @@ def conv_forward_small_cin(x, weight, stride, pad, dil, precise=False, **epi):
     return ops.conv2d_fwd(col, wp, 1, 0, 1, **epi), col
 
 
+def _direct_grad(param, shape_ohwi=None):
+    """The parameter's view of FlatSGD's gradient buffer when the optimizer asked for direct gradient writes (optim.FlatSGD,
+    direct_grads=True) and its memory is the dense OHWI / 1-D layout the kernels produce; else None."""
+    g = getattr(param, "_skd_grad", None)
+    if g is None:
+        return None
+    if shape_ohwi is not None:
+        cout, kh, kw, cin = shape_ohwi
+        if tuple(g.shape) != (cout, cin, kh, kw) or g.stride() != (kh * kw * cin, 1, kw * cin, cin):
+            return None
+    elif g.dim() != 1 or not g.is_contiguous():
+        return None
+    return g
+
+
+def _grad_written(param):
+    cb = getattr(param, "_skd_arrived", None)          # bucketed all-reduce bookkeeping (optim.FlatSGD.enable_overlap)
+    if cb is not None:
+        cb()
+
+
 class Conv2d(torch.autograd.Function):
     """nn.Conv2d forward / dgrad / wgrad on tcgen05.  x is NHWC-stored; weight is the (Cout,Cin,KH,KW) parameter held in
     channels-last (OHWI) storage."""
@@ -138,6 +159,7 @@ class Conv2d(torch.autograd.Function):
         else:
             y, xin = conv_forward_padded(x, weight, bias, stride, pad, dil)
         ctx.save_for_backward(xin, weight)
+        ctx.params = (weight, bias)                          # the Parameter objects (their flat gradient views hang on them)
         ctx.cfg = (stride, pad, dil, bias is not None, tuple(x.shape))
         return y
 
@@ -162,11 +184,22 @@ class Conv2d(torch.autograd.Function):
             dx = ops.conv2d_dgrad(dy, wp, (xshape[0], cin_p, xshape[2], xshape[3]), stride, pad, dil)
             if cin_p != cin:
                 dx = dx[:, :cin]
+        wparam, bparam = ctx.params
         if ctx.needs_input_grad[1]:
-            dw = ops.conv2d_wgrad(xin, dy, (kh, kw), stride, pad, dil)
-            dw = dw[:cout, :, :, :cin].permute(0, 3, 1, 2)
+            gview = _direct_grad(wparam, (cout, kh, kw, cin)) if (cout_p == cout and cin_p == cin) else None
+            if gview is not None:                            # wgrad (and its split-K reduction) writes the flat gradient buffer itself
+                ops.conv2d_wgrad(xin, dy, (kh, kw), stride, pad, dil, out=gview)
+                _grad_written(wparam)
+            else:
+                dw = ops.conv2d_wgrad(xin, dy, (kh, kw), stride, pad, dil)
+                dw = dw[:cout, :, :, :cin].permute(0, 3, 1, 2)
         if has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(dy)[:cout]
+            gview = _direct_grad(bparam) if cout_p == cout else None
+            if gview is not None:
+                ops.colsum(dy, out=gview)
+                _grad_written(bparam)
+            else:
+                db = ops.colsum(dy)[:cout]
         return dx, dw, db, None, None, None, None
 
 
@@ -188,6 +221,7 @@ class ABN(torch.autograd.Function):
         # output is not read again -- two HBM passes fewer per layer
         ctx.out_saved = residual is not None or activation == "elu"
         ctx.save_for_backward(x, out if ctx.out_saved else None, st, weight, chan_mul)
+        ctx.params = (weight, bias)
         ctx.cfg = (training, eps, activation, slope, residual is not None)
         return out
 
@@ -198,8 +232,16 @@ class ABN(torch.autograd.Function):
         training, eps, activation, slope, has_res = ctx.cfg
         # eval mode (libs/functions.py:144-147): edz = eydz = 0 -> dx = dz * gamma * rsqrt(var + eps), and -- a quirk of the
         # reference kept as is -- dweight = sign(w) * eydz * n = 0, dbias = edz * n = 0
+        wparam, bparam = ctx.params
+        gw = _direct_grad(wparam) if (training and ctx.needs_input_grad[1]) else None
+        gb = _direct_grad(bparam) if (training and ctx.needs_input_grad[2]) else None
+        if gw is None or gb is None:
+            gw = gb = None
         dx, dres, dw, db = ops.abn_backward(x, out, ops.to_nhwc(dout), st, weight, eps, activation, slope, chan_mul, has_res,
-                                            training=training)
+                                            training=training, dweight_out=gw, dbias_out=gb)
+        if gw is not None:                                   # the reduce kernel wrote dweight / dbias into the flat gradient buffer
+            _grad_written(wparam); _grad_written(bparam)
+            dw = db = None
         return dx, dw, db, None, None, None, None, None, None, None, dres, None
 
 

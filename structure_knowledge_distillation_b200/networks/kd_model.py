@@ -86,7 +86,7 @@ class NetModel():
         self.parallel_D = self.D_model
 
         self.G_solver = FlatSGD([p for p in self.student.parameters() if p.requires_grad], args.lr_g, momentum=args.momentum,
-                                weight_decay=args.weight_decay)
+                                weight_decay=args.weight_decay, direct_grads=True)
         self.D_solver = FlatSGD([p for p in self.D_model.parameters() if p.requires_grad], args.lr_d, momentum=args.momentum,
                                 weight_decay=args.weight_decay)
         self.best_mean_IU = _arg(args, "best_mean_IU", 0.0)

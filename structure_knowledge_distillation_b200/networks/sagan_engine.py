@@ -14,6 +14,8 @@ Activations are NHWC rows.  The 4x4/s2 spectral-norm convolutions and the q/k/v 
 kernel in split precision (3xTF32); weight gradients on the tcgen05 wgrad kernel (TF32); 1/sigma rides in the convolution
 epilogue's per-channel scale, so no normalised weight tensor is ever materialised.
 """
+import ctypes
+
 import torch
 
 from .. import ops
@@ -39,12 +41,20 @@ class _Tape:
     pass
 
 
+class _SnLayer(ctypes.Structure):
+    """struct skd_sn_layer (include/skd.h)"""
+    _fields_ = [("Cout", ctypes.c_int), ("taps", ctypes.c_int), ("Cin", ctypes.c_int), ("vec_len", ctypes.c_int),
+                ("w_bar", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p), ("u_save", ctypes.c_void_p),
+                ("v_save", ctypes.c_void_p), ("sigma", ctypes.c_void_p), ("inv_sigma_vec", ctypes.c_void_p)]
+
+
 class DiscEngine:
     """Bound to one `Discriminator` module; reads its parameters in place (FlatSGD views included)."""
 
     def __init__(self, D):
         self.D = D
         self.precise = True            # split-precision (3xTF32) forward / data-gradient convolutions
+        self.split_k = True            # split-K for the convolutions with too few output tiles to fill the GPU
         self._prep = None
         self._ws = None
 
@@ -120,8 +130,12 @@ class DiscEngine:
               residual=None, ldr=0, act=ACT_NONE, slope=0.0):
         if not self.precise:
             x_lo = wgt_lo = None
-        lib().skd_conv2d_fwd_sm100_ex(n, h, w, cin, cout, k, k, stride, pad, 1, _p(x), _p(x_lo), ldx, _p(wgt), _p(wgt_lo), _p(y), ldy,
-                                      out_hw[0], out_hw[1], _p(scale), _p(shift), _p(residual), ldr, act, slope, _st())
+        L = lib()
+        # few output tiles + long K (4x8 .. 16x32 maps): split-K over (tile, K range) units, partial planes in a workspace
+        nws = L.skd_conv2d_fwd_sm100_splitk_workspace_floats(n, h, w, cin, cout, k, k, stride, pad, 1, out_hw[0], out_hw[1]) if self.split_k else 0
+        ws = torch.empty(nws, device=y.device, dtype=torch.float32) if nws else None
+        L.skd_conv2d_fwd_sm100_splitk(n, h, w, cin, cout, k, k, stride, pad, 1, _p(x), _p(x_lo), ldx, _p(wgt), _p(wgt_lo), _p(y), ldy,
+                                      out_hw[0], out_hw[1], _p(scale), _p(shift), _p(residual), ldr, act, slope, _p(ws), nws, _st())
 
     def _split(self, t, rows=None):
         """lo part of the first `rows` leading entries of t (whole tensor by default), same shape as t"""
@@ -151,13 +165,17 @@ class DiscEngine:
         t.prep = prep
         # ---- spectral norm: one power iteration per layer; u, v advance in place (spectral.py:28-31)
         t.sn = []
-        for lay in prep["layers"]:
+        descs = (_SnLayer * len(prep["layers"]))()
+        for i, lay in enumerate(prep["layers"]):
             m = lay["m"]
             vec = max(lay["cout"], 4 * lay["cin_p"])
             s = dict(u=_f(lay["cout"], dev=dev), v=_f(16 * lay["cin"], dev=dev), sigma=_f(1, dev=dev), inv=_f(vec, dev=dev))
-            L.skd_sn_power_iter(lay["cout"], 16, lay["cin"], _p(m.weight_bar), _p(m.weight_u), _p(m.weight_v), _p(s["u"]), _p(s["v"]),
-                                _p(s["sigma"]), _p(s["inv"]), vec, st)
+            descs[i] = _SnLayer(lay["cout"], 16, lay["cin"], vec, _p(m.weight_bar), _p(m.weight_u), _p(m.weight_v), _p(s["u"]), _p(s["v"]),
+                                _p(s["sigma"]), _p(s["inv"]))
             t.sn.append(s)
+        # all four layers in one call: each phase of the iteration is a grid over every layer (csrc/disc.cu, sn_phase*_kernel)
+        sn_ws = _f(L.skd_sn_power_iter_batched_workspace_floats(len(descs), ctypes.cast(descs, ctypes.c_void_p)), dev=dev)
+        L.skd_sn_power_iter_batched(len(descs), ctypes.cast(descs, ctypes.c_void_p), _p(sn_ws), st)
         # ---- preprocess (sagan_models.py:147,157): BatchNorm2d with batch statistics in train mode
         bn = D.preprocess_additional
         Cp = ops.pad4(C)
@@ -300,7 +318,11 @@ class DiscEngine:
                 wsg = _f(max(nws, 4), dev=dev)
                 L.skd_conv2d_wgrad_sm100(nb, hin_hw[0], hin_hw[1], cin_p, cout, 4, 4, 2, 1, 1, _p(hin), cin_p, _p(g), cout, _p(dwn), _p(wsg), st)
                 dw, acc = self._grad_buf(sink, names[li] + ".weight_bar", m.weight_bar)
-                L.skd_sn_weight_grad(cout, 16, cin, cin_p, _p(dwn), _p(m.weight_bar), _p(s["u"]), _p(s["v"]), _p(s["sigma"]), _p(dw), acc,
+                # d sigma / d w_bar = u v^T with the module's CURRENT u, v, not this forward's: the reference rebinds `u.data` / `v.data`
+                # in every forward (spectral.py:30-31) and autograd's saved references to u and v see the latest values, so the backward
+                # of D(T) uses the vectors left by the last forward of the phase (D(S), or the penalty's D(interpolated)).  sigma itself
+                # is the value this forward computed.  (Visible at batch 1: the rank-one term is as large as the rest of l4's gradient.)
+                L.skd_sn_weight_grad(cout, 16, cin, cin_p, _p(dwn), _p(m.weight_bar), _p(m.weight_u), _p(m.weight_v), _p(s["sigma"]), _p(dw), acc,
                                      _p(ws["sn"]), st)
             if li == 0 and not need_input_adj:
                 return None
@@ -580,7 +602,7 @@ class SNConvFn(torch.autograd.Function):
             dwn = ops.conv2d_wgrad(x, dy, (kh, kw), m.stride, m.padding, m.dilation)
             dw = torch.empty_like(w_bar)
             ws = torch.zeros(L.skd_sn_weight_grad_workspace_doubles(), device=x.device, dtype=torch.float64)
-            L.skd_sn_weight_grad(cout, kh * kw, cin, cin, _p(dwn), _p(wq), _p(u), _p(v), _p(sigma), _p(dw), 0, _p(ws), st)
+            L.skd_sn_weight_grad(cout, kh * kw, cin, cin, _p(dwn), _p(wq), _p(m.weight_u), _p(m.weight_v), _p(sigma), _p(dw), 0, _p(ws), st)   # current u, v: see DiscEngine._reverse_layers
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = ops.colsum(dy)
         return None, dx, dw, db

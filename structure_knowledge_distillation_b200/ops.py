@@ -128,8 +128,9 @@ def abn_apply(x, scale, shift, act, slope, residual=None, chan_mul=None, out=Non
     return out
 
 
-def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dres, round_tf32=False, training=True):
-    """-> dx, dres (or None), dweight, dbias"""
+def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dres, round_tf32=False, training=True,
+                 dweight_out=None, dbias_out=None):
+    """-> dx, dres (or None), dweight, dbias.  dweight_out / dbias_out: write the affine gradients there (flat gradient views)."""
     n, c, h, w, pitch = nhwc_meta(x)
     if (out is not None and nhwc_meta(out)[4] != c) or nhwc_meta(dout)[4] != c or pitch != c:
         raise ValueError("Non-contiguous input")
@@ -140,16 +141,19 @@ def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dr
     ws = torch.empty(splits * c * 2, device=dev)
     if training:
         red = torch.empty(4, c, device=dev)          # edz, eydz, dweight, dbias
+        dwt = dweight_out if dweight_out is not None else red[2]
+        dbt = dbias_out if dbias_out is not None else red[3]
         L.skd_abn_bwd_reduce_nhwc(P, c, h * w, _p(x), _p(out), _p(dout), _p(stats[0]), _p(stats[1]), _p(weight), eps, ACT[act],
-                                  slope, _p(chan_mul), _p(red[0]), _p(red[1]), _p(red[2]), _p(red[3]), _p(ws), splits, _p(stats[2]), _p(stats[3]),
+                                  slope, _p(chan_mul), _p(red[0]), _p(red[1]), _p(dwt), _p(dbt), _p(ws), splits, _p(stats[2]), _p(stats[3]),
                                   _st())
     else:                                            # libs/functions.py:144-147: no batch-statistics terms, zero affine gradients
         red = torch.zeros(4, c, device=dev)
+        dwt, dbt = red[2], red[3]
     dx = empty_nhwc(n, c, h, w, dev)
     dres = empty_nhwc(n, c, h, w, dev) if want_dres else None
     L.skd_abn_bwd_dx_nhwc(P, c, h * w, _p(x), _p(out), _p(dout), _p(dx), _p(dres), _p(stats[0]), _p(stats[1]), _p(weight),
                           _p(red[0]), _p(red[1]), eps, ACT[act], slope, _p(chan_mul), int(round_tf32), _p(stats[2]), _p(stats[3]), _st())
-    return dx, dres, red[2], red[3]
+    return dx, dres, dwt, dbt
 
 
 # ------------------------------------------------------------------------------------------------ convolutions
@@ -276,13 +280,13 @@ def conv2d_dgrad(dy, w_ohwi, x_shape, stride, pad, dil, round_tf32=False, force_
     return dx
 
 
-def conv2d_wgrad(x, dy, kshape, stride, pad, dil, force_direct=False):
-    """dw in OHWI layout [Cout][KH][KW][Cin]."""
+def conv2d_wgrad(x, dy, kshape, stride, pad, dil, force_direct=False, out=None):
+    """dw in OHWI layout [Cout][KH][KW][Cin] (written into `out` when given: a dense OHWI buffer of that size)."""
     n, cin, h, w, ldx = nhwc_meta(x)
     dn, cout, doh, dow, ldy = nhwc_meta(dy)
     kh, kw = kshape
     L = lib()
-    dw = torch.empty((cout, kh, kw, cin), device=x.device, dtype=torch.float32)
+    dw = out if out is not None else torch.empty((cout, kh, kw, cin), device=x.device, dtype=torch.float32)
     if force_direct or cin % 4 or cout % 4 or ldx % 4 or ldy % 4:
         L.skd_conv2d_wgrad_direct(n, h, w, cin, cout, kh, kw, stride, pad, dil, _p(x), ldx, _p(dy), ldy, _p(dw), _st())
     else:
@@ -308,9 +312,9 @@ def im2col_small(x, kh, kw, stride, pad, dil, kp):
     return col
 
 
-def colsum(dy):
+def colsum(dy, out=None):
     n, c, h, w, ld = nhwc_meta(dy)
-    db = torch.empty(c, device=dy.device, dtype=torch.float32)
+    db = out if out is not None else torch.empty(c, device=dy.device, dtype=torch.float32)
     lib().skd_colsum(n * h * w, c, _p(dy), ld, _p(db), _st())
     return db
 

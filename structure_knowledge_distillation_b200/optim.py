@@ -25,7 +25,11 @@ def _dense(t):
 
 
 class FlatSGD:
-    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, direct_grads=False):
+        """direct_grads: the backward kernels of functions.py write each parameter's gradient straight into its view of the flat
+        buffer (`p._skd_grad`) instead of returning a tensor for autograd to add -- one elementwise launch and one temporary less
+        per parameter.  Valid because zero_grad() precedes every backward and no parameter is used twice in one forward; a caller
+        that accumulates several backward passes into .grad must leave it off."""
         self.params = [p for p in params]
         if not self.params:
             raise ValueError("optimizer got an empty parameter list")
@@ -49,6 +53,8 @@ class FlatSGD:
             g = torch.as_strided(self.flat_g, src.shape, src.stride(), off)
             p.grad = g
             self._views.append(g)
+            if direct_grads:
+                p._skd_grad = g
         self.lr_dev = torch.tensor(float(lr), device=dev, dtype=torch.float32)
         self.steps = 0
         self.grad_scale = 1.0
@@ -93,6 +99,7 @@ class FlatSGD:
         self._active = False
         for i, p in enumerate(self.params):
             p.register_post_accumulate_grad_hook(lambda _p, bi=which[i]: self._arrived(bi))
+            p._skd_arrived = (lambda bi=which[i]: self._arrived(bi))     # called by backward kernels that wrote p._skd_grad directly
 
     def begin_overlapped_reduce(self, world):
         self._world = world

@@ -450,6 +450,67 @@ def test_conv_backward(ops, case):
     assert rel(ops.conv2d_dgrad(dyc, wo, x.shape, s, p, d), x.grad) < 2e-3, "tcgen05 dgrad"
 
 
+@pytest.mark.parametrize("case", [(2, 64, 33, 31, 64, False), (1, 64, 64, 72, 128, False), (2, 128, 20, 17, 64, False), (1, 64, 129, 257, 64, False),
+                                  (1, 128, 65, 129, 128, False), (2, 32, 16, 8, 32, False), (1, 96, 19, 23, 100, False),
+                                  (2, 64, 33, 31, 64, True), (1, 64, 40, 37, 128, True), (1, 64, 129, 257, 64, True)])
+def test_conv3x3_halo_kernel(ops, case):
+    """conv_halo_sm100.cu: one halo tile per channel chunk, nine taps through shifted shared-memory descriptors.  Against float64
+    (TF32: 2e-3; split precision: 2e-5), with the fused scale / shift / ReLU epilogue, ragged tiles and zero padding at the borders;
+    and the dispatch inside skd_conv2d_fwd_sm100 agrees with the direct entry bit for bit."""
+    from structure_knowledge_distillation_b200._cabi import lib
+    L = lib()
+    N, Cin, H, W, Cout, precise = case
+    g = torch.Generator(device="cuda").manual_seed(N + Cin + H + W + Cout)
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) / (9 * Cin) ** 0.5
+    scale, shift = torch.rand(Cout, device="cuda", generator=g) + 0.5, torch.randn(Cout, device="cuda", generator=g) * 0.1
+    x_lo, w_lo = torch.empty_like(x), torch.empty_like(w)
+    L.skd_split_tf32(x.numel(), x.data_ptr(), None, x_lo.data_ptr(), _st()); L.skd_split_tf32(w.numel(), w.data_ptr(), None, w_lo.data_ptr(), _st())
+    y = torch.full((N, H, W, Cout), float("nan"), device="cuda")
+    L.skd_conv3x3_halo_sm100(N, H, W, Cin, Cout, x.data_ptr(), x_lo.data_ptr() if precise else None, Cin, w.data_ptr(),
+                             w_lo.data_ptr() if precise else None, y.data_ptr(), Cout, scale.data_ptr(), shift.data_ptr(), 3, 0.0, _st())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), None, 1, 1)
+    ref = torch.relu(ref * scale.double()[None, :, None, None] + shift.double()[None, :, None, None])
+    assert not torch.isnan(y).any()
+    e = rel(y.permute(0, 3, 1, 2), ref)
+    assert e < (2e-5 if precise else 2e-3), e
+    if not precise:
+        try:
+            L.skd_set_conv_halo(1)
+            y2 = ops.conv2d_fwd(x.permute(0, 3, 1, 2), w, 1, 1, 1, scale=scale, shift=shift, act="relu")
+            L.skd_set_conv_halo(0)
+            y3 = ops.conv2d_fwd(x.permute(0, 3, 1, 2), w, 1, 1, 1, scale=scale, shift=shift, act="relu")
+        finally:
+            L.skd_set_conv_halo(0)
+        assert torch.equal(y2.permute(0, 2, 3, 1), y)
+        assert rel(y3, y2) < 1e-3                                  # the general kernel: same TF32 products, another summation order
+
+
+@pytest.mark.parametrize("case", [(1, 256, 8, 8, 512, 4, 2, 1, 1), (2, 256, 8, 8, 512, 4, 2, 1, 1), (1, 128, 16, 16, 256, 4, 2, 1, 1),
+                                  (1, 20, 65, 65, 64, 4, 2, 1, 1), (1, 512, 4, 4, 640, 1, 1, 0, 1), (3, 64, 5, 3, 32, 3, 1, 1, 1)])
+def test_conv_wgrad_few_pixels(ops, case):
+    """Weight gradients whose K dimension (output pixels) is smaller than one K block of the tcgen05 kernel (16 .. 64 pixels:
+    the discriminator's top layers at batch 1-2): out-of-range pixels of the last box must contribute exact zeros."""
+    N, Cin, H, W, Cout, k, s, p, d = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case) + 7)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).double()
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).double().requires_grad_(True)
+    y = F.conv2d(x, w, None, s, p, d)
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(dy.double())
+    xc = ops.to_nhwc(x.float()); dyc = ops.to_nhwc(dy)
+    dw_ref = w.grad.permute(0, 2, 3, 1)
+    from structure_knowledge_distillation_b200._cabi import lib
+    for linear in (0, 1):
+        lib().skd_set_wgrad_linear(linear)
+        try:
+            e = rel(ops.conv2d_wgrad(xc, dyc, (k, k), s, p, d), dw_ref)
+        finally:
+            lib().skd_set_wgrad_linear(1)
+        assert e < 2e-3, ("tcgen05 wgrad", linear, e)
+
+
 # ---------------------------------------------------------------------------------------------- pools
 def test_stem_maxpool_and_psp_pyramid(ops):
     g = torch.Generator(device="cuda").manual_seed(3)

@@ -104,14 +104,14 @@ def test_distillation_step_matches_reference_golden(name):
             gs = g["samples"].double(); ms = mine[g["idx"].to(mine.device)].cpu()
             # the 16 sampled ELEMENTS: rel-L2 against the samples' own norm (floored at what 16 elements of a floor-sized tensor carry)
             e_s = float((ms - gs).norm() / max(float(gs.norm()), floor * (len(gs) / max(mine.numel(), len(gs))) ** 0.5))
-            table.append((pname, e, e_s))
+            table.append((pname, e, e_s, float(gs.norm()) / (g["norm"] * (len(gs) / max(mine.numel(), len(gs))) ** 0.5 + 1e-30)))
             if e > wd:
                 wd, wdn = e, pname
             if e_s > ws_:
                 ws_, wsn = e_s, pname
         report["worst_D_grad_norm_rel"] = (wd, wdn)
         report["worst_D_grad_samples_rel_l2"] = (ws_, wsn)
-        report["D_grad_table"] = " ".join("%s:%.1e/%.1e" % (n.replace(".0.module", "").replace("preprocess_additional", "bn"), a, b) for n, a, b in table if a > 0 or b > 0)
+        report["D_grad_table"] = " ".join("%s:%.1e/%.1e(x%.2f)" % (n.replace(".0.module", "").replace("preprocess_additional", "bn"), a, b, c) for n, a, b, c in table if a > 0 or b > 0)
     print("\nPARITY", name, {k: (("%.2e" % v) if isinstance(v, float) else v) for k, v in report.items()})
     full = name.startswith("baseline")
     # Contract (BASELINE.json): every loss within 1e-3 relative of the reference -- held at the benchmarked configuration
