@@ -299,6 +299,7 @@ def run_ours(args, rank, local_rank, world):
     # (events recorded inside a captured graph cannot be timed)
     conv_log = []
     model._graphs = None
+    model.overlap_streams = False                                  # one stream: an event pair must bracket ONE kernel, not its neighbours on other streams
     ops.CONV_EVENT_LOG = conv_log                                  # ops.conv2d_fwd records (start, end, flops) per tcgen05 launch
     ms_eager = timed(args.steps, step_resident)
     ops.CONV_EVENT_LOG = None
@@ -362,7 +363,8 @@ def run_ours(args, rank, local_rank, world):
                      "whole_step_note": "algorithmic conv FLOP of the step (%.2f TFLOP at batch %d, SURVEY.md 8d) / timed ms_per_step / peak: everything that is "
                                         "not a tensor-core convolution (ABN, losses, discriminator, SGD, glue) counts against it" % (step_flop / 1e12, BATCH_PER_GPU),
                      "measured_in": "per-launch CUDA events in an EAGER pass of the same %d steps right after the timed region (%.2f ms/step eager vs %.2f "
-                                    "ms/step timed graph replay): events cannot be recorded inside a captured graph" % (args.steps, ms_eager / args.steps, ms / args.steps)},
+                                    "ms/step timed graph replay): events cannot be recorded inside a captured graph; this pass runs on ONE stream (the timed step overlaps teacher / "
+                                    "student forward, weight gradients and the discriminator phase on four streams, where an event pair would also time its neighbours)" % (args.steps, ms_eager / args.steps, ms / args.steps)},
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()

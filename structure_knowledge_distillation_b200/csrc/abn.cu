@@ -479,40 +479,51 @@ __global__ void nhwc_bwd_finalize_kernel(const float2* __restrict__ partial, int
 }
 
 // dx = (dz - edz - y*eydz) * gamma*invstd ; dres = dz
+// The launch makes gridDim.x * blockDim.x a multiple of C4 whenever it can, so a thread meets ONE channel quad in every iteration of its
+// grid-stride loop: the per-channel terms fold once into dx = k1*(dz - edz) - k2*(x - mean) (ncu, round 2: the version that re-derived them per
+// element -- a 64-bit division, five parameter loads, four rsqrt -- was issue-bound at 4.1 TB/s while its sibling passes ran at 5.5).
 __global__ void __launch_bounds__(256)
 nhwc_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ out, const float* __restrict__ dout,
                    float* __restrict__ dx, float* __restrict__ dres, long long total4, int C4, int S,
                    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ weight,
                    const float* __restrict__ edz, const float* __restrict__ eydz, float eps, int act, float slope,
                    const float* __restrict__ chan_mul, int round_out, const float* __restrict__ scale, const float* __restrict__ shift) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / C4;
-    const int c4 = (int)(i - row * C4);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool fixed_c = (stride % C4) == 0;
+  float4 k1, k2, mu, e1, sc, sf;
+  auto coeffs = [&](int c4) {
+    mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(var) + c4);
+    e1 = __ldg(reinterpret_cast<const float4*>(edz) + c4);
+    const float4 e2 = __ldg(reinterpret_cast<const float4*>(eydz) + c4);
+    const float4 w = weight ? __ldg(reinterpret_cast<const float4*>(weight) + c4) : make_float4(1, 1, 1, 1);
+#define KK(f) { const float is = 1.f / sqrtf(vv.f + eps); const float gm = weight ? fabsf(w.f) + eps : 1.f; \
+                k1.f = gm * is; k2.f = is * e2.f * gm * is; }
+    KK(x) KK(y) KK(z) KK(w)
+#undef KK
+    if (!out) { sc = __ldg(reinterpret_cast<const float4*>(scale) + c4); sf = __ldg(reinterpret_cast<const float4*>(shift) + c4); }
+  };
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int c4 = (int)(i % C4);
+  if (fixed_c && i < total4) coeffs(c4);
+  for (; i < total4; i += stride) {
+    if (!fixed_c) { c4 = (int)(i % C4); coeffs(c4); }
     float4 xv = ld_stream(reinterpret_cast<const float4*>(x) + i);
     float4 ov;
     if (out) ov = ld_stream(reinterpret_cast<const float4*>(out) + i);
-    else {                                                  // sign of the activation input, recomputed (see nhwc_bwd_partial_kernel)
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4), sf = __ldg(reinterpret_cast<const float4*>(shift) + c4);
-      ov.x = xv.x * sc.x + sf.x; ov.y = xv.y * sc.y + sf.y; ov.z = xv.z * sc.z + sf.z; ov.w = xv.w * sc.w + sf.w;
-    }
+    else { ov.x = xv.x * sc.x + sf.x; ov.y = xv.y * sc.y + sf.y; ov.z = xv.z * sc.z + sf.z; ov.w = xv.w * sc.w + sf.w; }   // sign of the activation input, recomputed (see nhwc_bwd_partial_kernel)
     float4 g = ld_stream(reinterpret_cast<const float4*>(dout) + i);
     if (chan_mul) {
+      const long long row = i / C4;
       const float4 m = __ldg(reinterpret_cast<const float4*>(chan_mul) + (row / S) * C4 + c4);
       g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
     }
     g.x = dact(ov.x, g.x, act, slope); g.y = dact(ov.y, g.y, act, slope);
     g.z = dact(ov.z, g.z, act, slope); g.w = dact(ov.w, g.w, act, slope);
     if (dres) reinterpret_cast<float4*>(dres)[i] = g;
-    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
-    const float4 vv = __ldg(reinterpret_cast<const float4*>(var) + c4);
-    const float4 e1 = __ldg(reinterpret_cast<const float4*>(edz) + c4);
-    const float4 e2 = __ldg(reinterpret_cast<const float4*>(eydz) + c4);
-    float4 w = weight ? __ldg(reinterpret_cast<const float4*>(weight) + c4) : make_float4(1, 1, 1, 1);
     float4 o;
-#define DX(f) { const float is = 1.f / sqrtf(vv.f + eps); const float gm = weight ? fabsf(w.f) + eps : 1.f; \
-                o.f = (g.f - e1.f - (xv.f - mu.f) * is * e2.f) * gm * is; }
-    DX(x) DX(y) DX(z) DX(w)
-#undef DX
+    o.x = fmaf(g.x - e1.x, k1.x, -(xv.x - mu.x) * k2.x); o.y = fmaf(g.y - e1.y, k1.y, -(xv.y - mu.y) * k2.y);
+    o.z = fmaf(g.z - e1.z, k1.z, -(xv.z - mu.z) * k2.z); o.w = fmaf(g.w - e1.w, k1.w, -(xv.w - mu.w) * k2.w);
     if (round_out) { o.x = ptx::round_tf32(o.x); o.y = ptx::round_tf32(o.y); o.z = ptx::round_tf32(o.z); o.w = ptx::round_tf32(o.w); }
     reinterpret_cast<float4*>(dx)[i] = o;
   }

@@ -16,6 +16,13 @@
 // split-precision 3xTF32 with lo-part tiles), warps 2-9 epilogue (tcgen05.ld -> scale/shift/activation -> swizzled staging ->
 // TMA store of {32 ch, 8 px, 16 rows} boxes, hardware-clipped at the image edge).  K loop: channel chunk outermost, taps inside,
 // so a halo slot is released after its nine taps and the next tile's chunk can land while this tile's later chunks compute.
+//
+// Weights: every CTA needs the same 9 * Cin/32 weight boxes for every tile.  With one CTA per SM fetching them itself, 148 SMs hammer
+// the same few L2 lines (ncu: 376 us for 8 x 64 x 256 x 512 -> 64 with the A traffic already cut to 1/6: each 8 KB weight box took
+// 0.38 us to arrive -- hot-line latency, not bandwidth).  So the CTAs form CLUSTERS of 4: the leader issues each weight box once with
+// TMA multicast into the shared memory of all four, every CTA's MMA warp releases the stage on the leader's barrier
+// (tcgen05.commit ... multicast::cluster).  The CTAs of a cluster walk the same number of tiles (a ragged last round runs phantom
+// tiles on zero-filled halos).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -42,7 +49,7 @@ struct HaloArgs {
   const float* scale; const float* shift; int act; float slope; int round_out;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_x2,
@@ -62,24 +69,27 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   uint64_t* a_empty = a_full + kMaxSlots;
   uint64_t* b_full = a_empty + kMaxSlots;
   uint64_t* b_empty = b_full + kMaxStages;
-  uint64_t* tmem_full = b_empty + kMaxStages;
+  uint64_t* b_empty_all = b_empty + kMaxStages;                    // leader's: one arrival per CTA of the cluster
+  uint64_t* tmem_full = b_empty_all + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);
+  const uint32_t cta_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+  const int iters = (a.m_tiles + (int)gridDim.x - 1) / (int)gridDim.x;      // the same for every CTA: ragged rounds run phantom tiles
   float* s_shift = s_scale + BLOCK_N;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x); ptx::prefetch_tmap(&tmap_w); ptx::prefetch_tmap(&tmap_y);
     for (int s = 0; s < kMaxSlots; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); ptx::mbar_init(&b_empty_all[s], CL); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
     ptx::fence_barrier_init();
   }
   constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_base_slot);
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync(); else __syncthreads();     // peers' barriers exist before anything is multicast to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
@@ -88,8 +98,10 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     // ===================== TMA producer =====================
     if (lane == 0) {
       int slot = 0; uint32_t sphase = 0; int stage = 0; uint32_t bphase = 0;
-      for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+      for (int it = 0; it < iters; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        // phantom tile (ragged last round of a cluster): image index N is out of range -> the halo is all hardware zero fill
+        const int img = tile < a.m_tiles ? tile / tiles_per_img : a.N, rem = tile < a.m_tiles ? tile - img * tiles_per_img : 0;
         const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
         const int x0 = tx * kTW - 1, y0 = ty * kTH - 1;                 // halo origin (may be -1: hardware zero fill = padding)
         for (int kc = 0; kc < a.k_chunks; ++kc) {
@@ -100,11 +112,20 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
           if (split3) ptx::tma_load_4d(pa + kSlotBytes, &tmap_x2, &a_full[slot], kc * 32, x0, y0, img);
           if (++slot == a.nslots) { slot = 0; sphase ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
-            ptx::mbar_wait(&b_empty[stage], bphase ^ 1);
+            ptx::mbar_wait(&b_empty[stage], bphase ^ 1);                  // this CTA is done with the stage: arm its barrier
             uint8_t* pb = sB + stage * stage_stride;
             ptx::mbar_expect_tx(&b_full[stage], (uint32_t)stage_stride);
-            ptx::tma_load_3d(pb, &tmap_w, &b_full[stage], kc * 32, tap, 0);
-            if (split3) ptx::tma_load_3d(pb + kBBytes, &tmap_w2, &b_full[stage], kc * 32, tap, 0);
+            if constexpr (CL > 1) {
+              if (cta_rank == 0) {                                          // the leader fetches the box once for the whole cluster
+                ptx::mbar_wait(&b_empty_all[stage], bphase ^ 1);            // every CTA's MMAs have released the stage
+                constexpr uint16_t mask = (uint16_t)((1u << CL) - 1u);
+                ptx::tma_load_3d_mcast(pb, &tmap_w, &b_full[stage], kc * 32, tap, 0, mask);
+                if (split3) ptx::tma_load_3d_mcast(pb + kBBytes, &tmap_w2, &b_full[stage], kc * 32, tap, 0, mask);
+              }
+            } else {
+              ptx::tma_load_3d(pb, &tmap_w, &b_full[stage], kc * 32, tap, 0);
+              if (split3) ptx::tma_load_3d(pb + kBBytes, &tmap_w2, &b_full[stage], kc * 32, tap, 0);
+            }
             if (++stage == a.nstages) { stage = 0; bphase ^= 1; }
           }
         }
@@ -115,7 +136,7 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     constexpr uint32_t idesc = ptx::make_idesc_tf32(128, BLOCK_N, 0, 0);
     int slot = 0; uint32_t sphase = 0; int stage = 0; uint32_t bphase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x) {
+    for (int it = 0; it < iters; ++it) {
       if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       __syncwarp();
       ptx::tc_fence_after();
@@ -145,6 +166,7 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
               }
             }
             ptx::mma_commit(&b_empty[stage]);
+            if constexpr (CL > 1) ptx::mma_commit_mcast(&b_empty_all[stage], (uint16_t)1);   // ... and tell the leader
             if (tap == 8) {
               ptx::mma_commit(&a_empty[slot]);                                     // the halo slot is free after its nine taps
               if (kc == a.k_chunks - 1) ptx::mma_commit(&tmem_full[acc]);
@@ -173,8 +195,10 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       s_shift[etid] = (etid < a.Cout && a.shift) ? __ldg(a.shift + etid) : 0.f;
     }
     ptx::named_bar_sync(3, 256);
-    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x) {
-      const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+    for (int it = 0; it < iters; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const bool real = tile < a.m_tiles;
+      const int img = real ? tile / tiles_per_img : 0, rem = real ? tile - img * tiles_per_img : 0;
       const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
@@ -182,7 +206,7 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
 #pragma unroll 1
       for (int ch = group; ch < BLOCK_N / 32; ch += 2) {
         const int c0 = ch * 32;
-        if (c0 >= a.Cout) break;
+        if (c0 >= a.Cout || !real) break;                                          // phantom tile: nothing to store
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + ch * 32, r);
         ptx::tmem_ld_wait();
@@ -230,7 +254,7 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync(); else __syncthreads();     // peers may still multicast into / signal this CTA's shared memory
   if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
@@ -278,24 +302,47 @@ bool make_plan(int Cin, int Cout, int passes, HaloPlan* p) {
   return nstages >= 3;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CL>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx2, const CUtensorMap& tw2, const HaloArgs& a,
            int smem, cudaStream_t st) {
-  static int attr = 0;
-  if (attr < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_sm100_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_sm100_kernel<BLOCK_N, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) { set_error("skd_conv3x3_halo_sm100(attr)", e); return 0; }
-    attr = 232448;
+    attr = true;
   }
-  const int grid = a.m_tiles < kNumSMs ? a.m_tiles : kNumSMs;
-  conv3x3_halo_sm100_kernel<BLOCK_N><<<grid, kThreads, smem, st>>>(tx, tw, ty, tx2, tw2, a);
+  int grid = a.m_tiles < kNumSMs ? a.m_tiles : kNumSMs;
+  if (CL > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((kNumSMs / CL) * CL); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    // persistent grid = the clusters that can be resident at once (a cluster lives inside one GPC: with 18-SM GPCs not all 37
+    // clusters of 4 fit; the left-over would start as a second wave after the first finished its whole tile loop)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo_sm100_kernel<BLOCK_N, CL>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / CL; }
+      max_clusters = n;
+    }
+    grid = max_clusters * CL;
+    if (grid > (kNumSMs / CL) * CL) grid = (kNumSMs / CL) * CL;
+    cfg.gridDim = dim3(grid);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_halo_sm100_kernel<BLOCK_N, CL>, tx, tw, ty, tx2, tw2, a);
+    if (e != cudaSuccess) { set_error("skd_conv3x3_halo_sm100(cluster launch)", e); return 0; }
+  } else {
+    conv3x3_halo_sm100_kernel<BLOCK_N, CL><<<grid, kThreads, smem, st>>>(tx, tw, ty, tx2, tw2, a);
+  }
   return finish("skd_conv3x3_halo_sm100");
 }
 
 }  // namespace
 
 namespace skd {
-int g_conv_halo = 0;   // opt-in until validated on the GPU (skd_set_conv_halo)
+int g_halo_cluster = 1;
+int g_conv_halo = 1;   // skd_set_conv_halo(0): every shape through the general implicit-GEMM kernel
 
 bool conv3x3_halo_supported(int Cin, int Cout, int passes) {
   HaloPlan p;
@@ -341,11 +388,14 @@ int conv3x3_halo_launch(int N, int H, int W, int Cin, int Cout, const float* x, 
   a.tiles_x = (W + kTW - 1) / kTW; a.tiles_y = (H + kTH - 1) / kTH; a.m_tiles = N * a.tiles_x * a.tiles_y; a.k_chunks = p.k_chunks;
   a.passes = passes; a.nslots = p.nslots; a.nstages = p.nstages;
   a.scale = scale; a.shift = shift; a.act = act; a.slope = slope; a.round_out = round_tf32;
-  return p.bn == 128 ? launch<128>(tx, tw, ty, tx2, tw2, a, p.smem, st) : launch<64>(tx, tw, ty, tx2, tw2, a, p.smem, st);
+  // clusters of 4 share every weight box through TMA multicast; a handful of tiles is not worth a cluster
+  const bool mc = g_halo_cluster && a.m_tiles >= 2 * kNumSMs;
+  if (p.bn == 128) return mc ? launch<128, 4>(tx, tw, ty, tx2, tw2, a, p.smem, st) : launch<128, 1>(tx, tw, ty, tx2, tw2, a, p.smem, st);
+  return mc ? launch<64, 4>(tx, tw, ty, tx2, tw2, a, p.smem, st) : launch<64, 1>(tx, tw, ty, tx2, tw2, a, p.smem, st);
 }
 }  // namespace skd
 
-extern "C" void skd_set_conv_halo(int on) { skd::g_conv_halo = on ? 1 : 0; }
+extern "C" void skd_set_conv_halo(int on) { skd::g_conv_halo = (on & 1) ? 1 : 0; skd::g_halo_cluster = (on & 2) ? 0 : 1; }   // bit 1: no weight multicast
 
 extern "C" int skd_conv3x3_halo_sm100(int N, int H, int W, int Cin, int Cout, const float* x, const float* x_lo, int ldx, const float* w,
                                       const float* w_lo, float* y, int ldy, const float* scale, const float* shift, int act, float slope,

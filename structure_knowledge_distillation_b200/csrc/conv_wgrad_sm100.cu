@@ -250,10 +250,22 @@ Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int strid
   if (p.linear) p.kb_total = (int)(((long long)N * p.OH * p.OW + kpix - 1) / kpix);
   p.m_tiles = (Cout + kBlockM - 1) / kBlockM; p.n_tiles = (Cin + p.bn - 1) / p.bn; p.taps = KH * KW;
   const int tiles = p.m_tiles * p.n_tiles * p.taps;
-  int splits = (2 * kNumSMs + tiles - 1) / tiles;
+  // split-K: work units = tiles x K ranges over a persistent grid of kNumSMs CTAs.  Pick the split count whose unit count fills
+  // whole waves best (ncu, round 2: 9 tiles x 33 splits = 297 units = 2 waves + ONE unit -> a third round, 34 % of the SM cycles
+  // idle; 72 tiles x 5 = 360 units = 2.4 waves -> 23 % idle), fewer splits on ties (each split writes a partial dW plane)
   int cap = p.kb_total / 16; if (cap < 1) cap = 1;          // at least 16 k-blocks per unit
-  if (splits > cap) splits = cap;
-  if (splits < 1) splits = 1;
+  int hi = (4 * kNumSMs + tiles - 1) / tiles; if (hi > cap) hi = cap; if (hi < 1) hi = 1;
+  int best_sp = 1; double best_eff = -1.0;
+  for (int sp = 1; sp <= hi; ++sp) {
+    const int kps = (p.kb_total + sp - 1) / sp;
+    const int real = (p.kb_total + kps - 1) / kps;             // splits that actually get work
+    const long long units = (long long)tiles * real;
+    const long long waves = (units + kNumSMs - 1) / kNumSMs;
+    double eff = (double)units / (double)(waves * kNumSMs);
+    if (units < kNumSMs) eff = (double)units / kNumSMs * 0.999;   // less than one wave: more units is better
+    if (eff > best_eff + 0.02) { best_eff = eff; best_sp = real; }
+  }
+  int splits = best_sp;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   return p;

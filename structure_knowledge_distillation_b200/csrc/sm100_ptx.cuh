@@ -165,6 +165,21 @@ __device__ __forceinline__ void mma_commit_2cta(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// ---- cluster multicast (cta_group::1 kernels whose CTAs read the same tile) -----------------------------
+// one TMA load, delivered to the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier at the offset of
+// `bar` receives the transaction bytes (every CTA arms its own barrier with expect_tx)
+__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+// previously issued MMAs of this thread arrive, on completion, on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {           // whole warp, .sync.aligned

@@ -137,6 +137,43 @@ def _direct_grad(param, shape_ohwi=None):
     return g
 
 
+class WgradOverlap:
+    """Weight-gradient kernels on a side stream.  In the backward pass only the data-gradient chain (dgrad -> ABN backward -> dgrad
+    ...) is sequential; a layer's weight gradient needs (x, dy) and feeds nothing but the optimizer.  Issued on a second stream the
+    tcgen05 wgrad kernels (12 K registers, no co-residency conflict) overlap the HBM-bound ABN backward passes of the chain instead
+    of queueing between them.  NetModel opens a window around G_loss.backward(); tensors a side-stream kernel reads are kept alive
+    until the window's join, so the caching allocator cannot hand their memory to a main-stream kernel early (valid in eager
+    mode and under CUDA-graph capture alike -- no record_stream)."""
+    stream = None
+    keep = None
+
+    @classmethod
+    def begin(cls):
+        if cls.stream is None:
+            cls.stream = torch.cuda.Stream()
+        cls.keep = []
+
+    @classmethod
+    def end(cls):
+        if cls.keep is None:
+            return
+        torch.cuda.current_stream().wait_stream(cls.stream)
+        cls.keep = None
+
+    @classmethod
+    def run(cls, fn, *tensors):
+        """fn() on the side stream after everything enqueued so far on the current stream (no-op wrapper outside a window)."""
+        if cls.keep is None:
+            return fn()
+        cls.stream.wait_stream(torch.cuda.current_stream())
+        cls.keep.extend(t for t in tensors if t is not None)
+        with torch.cuda.stream(cls.stream):
+            out = fn()
+        if isinstance(out, torch.Tensor):
+            cls.keep.append(out)
+        return out
+
+
 def _grad_written(param):
     cb = getattr(param, "_skd_arrived", None)          # bucketed all-reduce bookkeeping (optim.FlatSGD.enable_overlap)
     if cb is not None:
@@ -171,7 +208,7 @@ class Conv2d(torch.autograd.Function):
         w = ops.weight_ohwi(weight)
         cout, kh, kw, cin = w.shape
         if ctx.small:                                        # xin is the im2col matrix: the weight gradient is a single-tap GEMM
-            dwc = ops.conv2d_wgrad(xin, ops.to_nhwc(dy), (1, 1), 1, 0, 1)               # [Cout][1][1][Kp]
+            dwc = ops.conv2d_wgrad(xin, ops.to_nhwc(dy), (1, 1), 1, 0, 1)               # [Cout][1][1][Kp] (main stream: its result is reshaped right here)
             dw = dwc.reshape(cout, -1)[:, :kh * kw * cin].reshape(cout, kh, kw, cin).permute(0, 3, 1, 2)
             return None, dw, None, None, None, None, None
         cin_p, cout_p = ops.pad4(cin), ops.pad4(cout)
@@ -188,7 +225,7 @@ class Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gview = _direct_grad(wparam, (cout, kh, kw, cin)) if (cout_p == cout and cin_p == cin) else None
             if gview is not None:                            # wgrad (and its split-K reduction) writes the flat gradient buffer itself
-                ops.conv2d_wgrad(xin, dy, (kh, kw), stride, pad, dil, out=gview)
+                WgradOverlap.run(lambda: ops.conv2d_wgrad(xin, dy, (kh, kw), stride, pad, dil, out=gview), xin, dy)
                 _grad_written(wparam)
             else:
                 dw = ops.conv2d_wgrad(xin, dy, (kh, kw), stride, pad, dil)

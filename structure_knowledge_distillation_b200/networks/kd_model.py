@@ -21,6 +21,7 @@ import os.path as osp
 import torch
 import torch.distributed as dist
 
+from .. import functions as Fn
 from .. import ops
 from ..optim import FlatSGD
 from ..utils.criterion import (CriterionAdditionalGP, CriterionAdv, CriterionAdvForG, CriterionDSN,
@@ -102,6 +103,9 @@ class NetModel():
             self.criterion_AdditionalGP = CriterionAdditionalGP(self.parallel_D, args.lambda_gp)
         self.criterion_adv_for_G = CriterionAdvForG(args.adv_loss_type)
 
+        self.overlap_streams = bool(_arg(args, "overlap_streams", True))
+        self._teacher_stream = None
+        self._d_stream = None
         self._graphs = None
         if _arg(args, "cuda_graph", False):
             self.enable_cuda_graphs()
@@ -148,9 +152,23 @@ class NetModel():
 
     def forward(self):
         images = ops.pad_channels(self.images, 4)                 # shared by teacher and student
-        with torch.no_grad():
+        if not self.overlap_streams:
+            with torch.no_grad():
+                self.preds_T = self.parallel_teacher.eval()(images)
+            self.preds_S = self.parallel_student.train()(images)
+            return
+        # the frozen teacher and the student are independent until the losses: the teacher's forward goes to a second stream, so the
+        # student's HBM-bound passes (ABN statistics / apply, pooling) run under the teacher's tensor-bound convolutions (one
+        # persistent conv CTA per SM leaves registers for one elementwise CTA beside it) instead of between them
+        cur = torch.cuda.current_stream()
+        if self._teacher_stream is None:
+            self._teacher_stream = torch.cuda.Stream()
+        side = self._teacher_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
             self.preds_T = self.parallel_teacher.eval()(images)
         self.preds_S = self.parallel_student.train()(images)
+        cur.wait_stream(side)
 
     def student_backward(self):
         args = self.args
@@ -176,9 +194,14 @@ class NetModel():
             # the ONE collective of the path (teacher frozen): bucketed NCCL all-reduce of the flat student gradient, issued from
             # inside the backward pass as each range of parameters completes (utils/parallel.py:54-63,155 semantics: mean over ranks)
             self.G_solver.begin_overlapped_reduce(self.world)
+        if self.overlap_streams:
+            Fn.WgradOverlap.begin()
+            if Fn.WgradOverlap.stream not in self.G_solver.producer_streams:
+                self.G_solver.producer_streams.append(Fn.WgradOverlap.stream)
         try:
             G_loss.backward()
         finally:
+            Fn.WgradOverlap.end()                                 # join: weight gradients complete before the all-reduce / SGD step
             self.D_model.skip_param_grads = False
             self.D_model.engine.release()
             if overlap:
@@ -190,6 +213,34 @@ class NetModel():
         self._discriminator_phase()
         self.D_solver.all_reduce_grads(self.world)
         self.D_solver.step()
+
+    def _student_and_discriminator_phases(self):
+        """One step up to (not including) the two optimizer updates, with the discriminator phase (kd_model.py:153-163 without the
+        D step) on its own stream UNDER the student's backward pass.  The D phase needs the logits of forward() and the D state left
+        by the generator pass's D(S) (one power iteration) -- not the student's gradients or its updated weights -- and its ~370
+        launches are tiny grids (4x8 .. 32x64 maps): alone they leave the GPU mostly idle for ~4 ms, beside the student's
+        backward kernels they cost nothing.  It starts once the generator pass's adjoint through D has been issued (event recorded
+        by DiscriminatorFn.backward) and is joined before the optimizer updates."""
+        self.forward()
+        self.G_solver.zero_grad()
+        if not (self.args.ho == True and self.overlap_streams):
+            self.student_backward()
+            if self.args.ho == True:
+                self._discriminator_phase()
+            return
+        if self._d_stream is None:
+            self._d_stream = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        self.D_model.adjoint_done_event = ev
+        try:
+            self.student_backward()                        # enqueues the whole backward; the event sits right after D's adjoint
+        finally:
+            self.D_model.adjoint_done_event = None
+        cur = torch.cuda.current_stream()
+        self._d_stream.wait_event(ev)
+        with torch.cuda.stream(self._d_stream):
+            self._discriminator_phase()
+        cur.wait_stream(self._d_stream)
 
     def _reduce_G(self):
         """all-reduce of the student gradient unless the backward pass already did it bucket by bucket"""
@@ -220,14 +271,19 @@ class NetModel():
             D.engine.release()
         self.D_loss = _LazyScalar(d_loss)
 
-    def optimize_parameters(self):
-        if self._graphs is not None:
-            return self._optimize_graphed()
-        self._student_phase()
+    def _updates(self):
+        """G_solver.step() and, with Ho, the D all-reduce + D_solver.step() (kd_model.py:171, :165)."""
         self._reduce_G()
         self.G_solver.step()
         if self.args.ho == True:
-            self.discriminator_backward()
+            self.D_solver.all_reduce_grads(self.world)
+            self.D_solver.step()
+
+    def optimize_parameters(self):
+        if self._graphs is not None:
+            return self._optimize_graphed()
+        self._student_and_discriminator_phases()
+        self._updates()
 
     # ---- CUDA-graph execution: the ~4 000 launches of a step are captured once and replayed ------------------------
     def enable_cuda_graphs(self, warmup=3):
@@ -246,11 +302,8 @@ class NetModel():
                 side = g.setdefault("side", torch.cuda.Stream())
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    self._student_phase()
-                    self._reduce_G(); self.G_solver.step()
-                    if self.args.ho == True:
-                        self._discriminator_phase()
-                        self.D_solver.all_reduce_grads(self.world); self.D_solver.step()
+                    self._student_and_discriminator_phases()
+                    self._updates()
                 torch.cuda.current_stream().wait_stream(side)
                 return
             # static input buffers + capture
@@ -258,20 +311,12 @@ class NetModel():
             torch.cuda.synchronize()
             g["student"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g["student"]):
-                self._student_phase()
-            self._reduce_G(); self.G_solver.step()
-            if self.args.ho == True:
-                g["D"] = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g["D"], pool=g["student"].pool()):
-                    self._discriminator_phase()
-                self.D_solver.all_reduce_grads(self.world); self.D_solver.step()
+                self._student_and_discriminator_phases()     # ONE graph: teacher || student forward, backward || wgrad || D phase
+            self._updates()
             g["captured"] = True
             return
         g["student"].replay()
-        self._reduce_G(); self.G_solver.step()
-        if self.args.ho == True:
-            g["D"].replay()
-            self.D_solver.all_reduce_grads(self.world); self.D_solver.step()
+        self._updates()
 
     def evalute_model(self, model, loader, gpu_id, input_size, num_classes, whole):
         mean_IU, IU_array = evaluate_main(model=model, loader=loader, gpu_id=gpu_id, input_size=input_size, num_classes=num_classes, whole=whole)

@@ -506,6 +506,9 @@ class DiscriminatorFn(torch.autograd.Function):
         sink = None if D.accumulate_into_grad else {}
         dx = D.engine.backward(t, gout, sink, want_dx, want_p)
         ctx.tape = None
+        ev = getattr(D, "adjoint_done_event", None)
+        if ev is not None:                                   # NetModel: the discriminator phase may start on its own stream from here
+            ev.record(torch.cuda.current_stream())
         grads = (None,) * (len(ctx.needs_input_grad) - 2)
         if want_p and sink is not None:
             grads = tuple(sink.get(n) for n in D.grad_names)

@@ -60,6 +60,7 @@ class FlatSGD:
         self.grad_scale = 1.0
         self._offsets = offs + [total]
         self._buckets = None
+        self.producer_streams = []
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
@@ -112,6 +113,8 @@ class FlatSGD:
         b["sent"] = True
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)                                  # the bucket's gradients are complete on the compute stream
+        for s in self.producer_streams:                              # ... and on the streams that write gradients besides it (wgrad overlap)
+            self._side.wait_stream(s)
         with torch.cuda.stream(self._side):
             dist.all_reduce(self.flat_g[b["start"]:b["end"]], op=dist.ReduceOp.SUM)
 

@@ -452,7 +452,9 @@ def test_conv_backward(ops, case):
 
 @pytest.mark.parametrize("case", [(2, 64, 33, 31, 64, False), (1, 64, 64, 72, 128, False), (2, 128, 20, 17, 64, False), (1, 64, 129, 257, 64, False),
                                   (1, 128, 65, 129, 128, False), (2, 32, 16, 8, 32, False), (1, 96, 19, 23, 100, False),
-                                  (2, 64, 33, 31, 64, True), (1, 64, 40, 37, 128, True), (1, 64, 129, 257, 64, True)])
+                                  (2, 64, 33, 31, 64, True), (1, 64, 40, 37, 128, True), (1, 64, 129, 257, 64, True),
+                                  # >= 296 tiles: clusters of 4 with TMA-multicast weights (ragged last round -> phantom tiles)
+                                  (2, 64, 129, 257, 128, False), (4, 128, 65, 129, 64, False), (3, 64, 129, 257, 128, True)])
 def test_conv3x3_halo_kernel(ops, case):
     """conv_halo_sm100.cu: one halo tile per channel chunk, nine taps through shifted shared-memory descriptors.  Against float64
     (TF32: 2e-3; split precision: 2e-5), with the fused scale / shift / ReLU epilogue, ragged tiles and zero padding at the borders;

@@ -87,8 +87,39 @@ def test_distillation_step_matches_reference_golden(name):
     report["worst_student_grad_samples_rel_l2"] = (worst_s, worst_s_name)
     m.G_solver.step()
     if cfg.ho:
+        d_state = {k: v.detach().clone() for k, v in m.D_model.state_dict().items()}     # after the generator pass's power iteration
         m.discriminator_backward()
         report["D"] = _relerr(m.D_loss, gold["D"])
+        # (1) the discriminator phase ON IDENTICAL INPUTS: oracle/port.py in float64 (autograd, double backward for the penalty) fed
+        # with OUR teacher / student logits and the same D state -- isolates this phase from the student's TF32 logit perturbation,
+        # to which the golden's D gradients are very sensitive on the batch-1 cases (one 4x4 map at the top of D)
+        from oracle import port
+        Dq = port.Discriminator(1, 19, 64)
+        Dq.load_state_dict({k: v.cpu() for k, v in d_state.items()})
+        Dq = Dq.cuda().double().train()
+        tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            ls, lt = m.preds_S[0].detach().double().contiguous(), m.preds_T[0].detach().double().contiguous()
+            dT, dS = Dq(lt), Dq(ls)                                                     # kd_model.py:156-157 order
+            dl = cfg.lambda_d * port.adv_loss_d(dS, dT, cfg.adv_type)
+            if cfg.adv_type == "wgan-gp":
+                dl = dl + cfg.lambda_d * port.gradient_penalty(Dq, ls, lt, m.criterion_AdditionalGP.alpha.double(), cfg.lambda_gp)
+            dl.backward()
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+        report["D_same_inputs"] = _relerr(m.D_loss, dl)
+        refs = dict(Dq.named_parameters())
+        topq = max(float(q.grad.norm()) for q in refs.values() if q.grad is not None)
+        wq, wqn = 0.0, None
+        for pname, p in m.D_model.named_parameters():
+            q = refs.get(pname)
+            if q is None or q.grad is None or p.grad is None:
+                continue
+            e = float((p.grad.detach().double() - q.grad).norm() / max(float(q.grad.norm()), 1e-3 * topq))
+            if e > wq:
+                wq, wqn = e, pname
+        report["worst_D_grad_rel_l2_same_inputs"] = (wq, wqn)
         # per-tensor comparison.  Gradients that cancel analytically (attention gammas at their zero init: <gy, O> summed over
         # positions of both signs; last.0.bias: +mean - mean) are round-off residue 3-4 orders below the other tensors in the
         # reference's own fp32 run, so every denominator is floored at 1e-3 of the largest gradient norm of the step
@@ -132,8 +163,14 @@ def test_distillation_step_matches_reference_golden(name):
     assert report["student_grad_samples_cosine"] > (0.99 if full else 0.93)
     if cfg.ho:
         # D's gradients depend on the student logits (3e-2 rel-L2 on the small random-init cases, 5e-3 at the benchmark config)
+        # on identical inputs: whole-tensor rel-L2 of every D gradient (LeakyReLU sign flips of single activations at batch 1-2 are
+        # the floor: a 0.9 jump of one of 16 384 top-layer activations is 7e-3)
+        assert report["D_same_inputs"] < 1e-4, report["D_same_inputs"]
+        assert report["worst_D_grad_rel_l2_same_inputs"][0] < 3e-2, report["worst_D_grad_rel_l2_same_inputs"]
+        # against the golden (the reference's own logits as D inputs): norms everywhere, sampled elements at the benchmark config
         assert report["worst_D_grad_norm_rel"][0] < (0.05 if full else 0.3), report["worst_D_grad_norm_rel"]
-        assert report["worst_D_grad_samples_rel_l2"][0] < (0.1 if full else 0.3), report["worst_D_grad_samples_rel_l2"]
+        if full:
+            assert report["worst_D_grad_samples_rel_l2"][0] < 0.1, report["worst_D_grad_samples_rel_l2"]
 
 
 def _snapshot(m):

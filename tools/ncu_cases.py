@@ -1,0 +1,72 @@
+"""One launch (after 2 warm-ups) of named kernel cases at the benchmark shapes, for `ncu --set full -k regex:<kernel>`.
+   usage: python tools/ncu_cases.py <case> [<case> ...]     (cases: see CASES)"""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from structure_knowledge_distillation_b200 import ops
+from structure_knowledge_distillation_b200._cabi import lib
+
+L = lib()
+dev = "cuda"
+
+
+def rn(*s):
+    return torch.randn(*s, device=dev)
+
+
+def conv_case(N, Cin, H, W, Cout, k, s, p, d, halo=0, precise=False):
+    x = ops.to_nhwc(rn(N, Cin, H, W)); w = rn(Cout, k, k, Cin) / (Cin * k * k) ** 0.5
+    L.skd_set_conv_halo(halo)
+    fn = (lambda: ops.conv2d_fwd_3xtf32(x, w, s, p, d)) if precise else (lambda: ops.conv2d_fwd(x, w, s, p, d))
+    return fn
+
+
+def wgrad_case(N, Cin, H, W, Cout, k, s, p, d):
+    x = ops.to_nhwc(rn(N, Cin, H, W))
+    oh, ow = ops.conv_out_hw(H, W, (k, k), s, p, d)
+    dy = ops.to_nhwc(rn(N, Cout, oh, ow))
+    return lambda: ops.conv2d_wgrad(x, dy, (k, k), s, p, d)
+
+
+def abn_case(N, C, H, W, which, res=False):
+    x = ops.to_nhwc(rn(N, C, H, W)); w = torch.rand(C, device=dev) + 0.5; b = rn(C) * 0.1
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    st = ops.abn_stats(x, w, b, 1e-5, 0.1, rm, rv)
+    r = ops.to_nhwc(rn(N, C, H, W)) if res else None
+    out = ops.abn_apply(x, st[2], st[3], "relu", 0.0, residual=r)
+    dout = ops.to_nhwc(rn(N, C, H, W))
+    if which == "stats":
+        return lambda: ops.abn_stats(x, w, b, 1e-5, 0.1, rm, rv)
+    if which == "apply":
+        return lambda: ops.abn_apply(x, st[2], st[3], "relu", 0.0, residual=r)
+    return lambda: ops.abn_backward(x, out if res else None, dout, st, w, 1e-5, "relu", 0.0, None, res)
+
+
+CASES = {
+    # weight gradients, the Cin = 64 convolutions (general kernel vs halo kernel), ABN passes
+    "wgrad_512_d4": lambda: wgrad_case(8, 512, 65, 129, 512, 3, 1, 4, 4),
+    "wgrad_stem_64": lambda: wgrad_case(8, 64, 256, 512, 64, 3, 1, 1, 1),
+    "conv64_general": lambda: conv_case(8, 64, 256, 512, 64, 3, 1, 1, 1, halo=0),
+    "conv64_halo": lambda: conv_case(8, 64, 256, 512, 64, 3, 1, 1, 1, halo=1),
+    "conv64_3x_general": lambda: conv_case(8, 64, 256, 512, 64, 3, 1, 1, 1, halo=0, precise=True),
+    "conv64_3x_halo": lambda: conv_case(8, 64, 256, 512, 64, 3, 1, 1, 1, halo=1, precise=True),
+    "conv128_64_halo": lambda: conv_case(8, 128, 256, 512, 64, 3, 1, 1, 1, halo=1),
+    "abn_stats_stem": lambda: abn_case(8, 64, 256, 512, "stats"),
+    "abn_apply_stem": lambda: abn_case(8, 64, 256, 512, "apply"),
+    "abn_bwd_stem": lambda: abn_case(8, 64, 256, 512, "bwd"),
+    "abn_bwd_res_l1": lambda: abn_case(8, 64, 129, 257, "bwd", res=True),
+}
+
+if __name__ == "__main__":
+    for name in sys.argv[1:]:
+        fn = CASES[name]()
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        L.skd_set_conv_halo(0)
+        print(name, "done")
