@@ -149,7 +149,7 @@ int skd_conv2d_fwd_sm100_splitk(int N, int H, int W, int Cin, int Cout, int KH, 
    loaded once per 32-channel chunk and the nine taps read it through shifted shared-memory descriptors -- the general kernel moves
    every activation line L2 -> shared memory nine times and is L2-bound at these widths.  skd_conv2d_fwd_sm100 / _3xtf32 / _ex route
    eligible shapes here by themselves (skd_set_conv_halo(0) turns that off); this entry calls it directly.  x_lo / w_lo as in _ex. */
-void skd_set_conv_halo(int on);
+void skd_set_conv_halo(int on);   /* bit 0: route eligible shapes to the halo kernel (default 1); bit 2: clusters of 4 with TMA-multicast weights (default off: slower) */
 int skd_conv3x3_halo_sm100(int N, int H, int W, int Cin, int Cout, const float* x, const float* x_lo, int ldx, const float* w,
                            const float* w_lo, float* y, int ldy, const float* scale, const float* shift, int act, float slope, cudaStream_t);
 
@@ -179,6 +179,7 @@ int skd_weight_flip_transpose(int Cout, int Cin, int KH, int KW, const float* w,
 int skd_round_tf32(long long n, const float* src, float* dst, cudaStream_t);
 void skd_set_tf32_tma_type(int use_tfloat32_type);
 void skd_set_wgrad_linear(int on);     /* 1 (default): wgrad K-blocks are 32 consecutive pixels (im2col TMA); 0: 4x8 rectangles */
+void skd_set_wgrad_cta_pairs(int on);   /* 1 (default): cta_group::2 pairs (256 x 256 tiles) where Cout % 256 == 0 and Cin > 128 */
 void skd_set_conv_res_prefetch(int on); /* 1 (default): residual tiles arrive through a TMA ring in spare pipeline-stage buffers */
 void skd_set_conv_tile_order(int mode); /* 0 (default) front-to-back, 1 back-to-front, 2 alternate per launch (a consumer starts on
                                           the tail its producer left in L2) */

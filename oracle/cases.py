@@ -65,6 +65,14 @@ FULL_CASES = {
 }
 
 
+# BASELINE.json configs[3] shape (360x480 CamVid crops -> 46x61 logits), ResNet18 student (the reference ships no ESPNet source).
+# Pi+Pa only: the reference's own discriminator cannot run on 46x61 logits (sagan_models.py:131-136,163); our size-aware head is
+# checked against oracle/port.py with the same head in tests/test_discriminator_gpu.py.  `python -m oracle.make_golden --cfg4`.
+CFG4_CASES = {
+    "cfg4_pi_pa_360x480_b2": dict(batch=2, h=360, w=480, cfg=dict(pi=True, pa=True, ho=False, pool_scale=0.5)),
+}
+
+
 def grad_digest(named_params, k=16):
     """Small fingerprint of each gradient: l2 norm, sum, and k strided samples."""
     out = {}

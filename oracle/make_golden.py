@@ -192,6 +192,9 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref = refshim.load_reference()
     torch.set_num_threads(os.cpu_count())
+    if "--cfg4" in sys.argv:
+        torch.save(step_goldens(ref, cases.CFG4_CASES), os.path.join(GOLDEN_DIR, "steps_cfg4.pt"))
+        return
     if "--full" in sys.argv:
         torch.save(step_goldens(ref, cases.FULL_CASES, check_port=False), os.path.join(GOLDEN_DIR, "steps_full.pt"))
         return

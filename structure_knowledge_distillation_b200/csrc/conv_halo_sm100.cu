@@ -22,7 +22,12 @@
 // 0.38 us to arrive -- hot-line latency, not bandwidth).  So the CTAs form CLUSTERS of 4: the leader issues each weight box once with
 // TMA multicast into the shared memory of all four, every CTA's MMA warp releases the stage on the leader's barrier
 // (tcgen05.commit ... multicast::cluster).  The CTAs of a cluster walk the same number of tiles (a ragged last round runs phantom
-// tiles on zero-filled halos).
+// tiles on zero-filled halos).  MEASURED: slower than every CTA fetching for itself (the leader can refill a stage only when all
+// four CTAs have released it: lock-step) -- kept as an option (skd_set_conv_halo bit 2), off by default.
+//
+// What does work where it fits (Cin, Cout <= 64, TF32: 144 KB of weights): WRES -- the whole filter bank is loaded ONCE per persistent
+// CTA and stays in shared memory; only halo tiles stream.  The weight ring was latency-bound, not bandwidth-bound: 8 stages x 8 KB in
+// flight against ~2.5 us of loaded L2 latency is ~25 GB/s per SM where the tensor core wants ~80.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -49,7 +54,7 @@ struct HaloArgs {
   const float* scale; const float* shift; int act; float slope; int round_out;
 };
 
-template <int BLOCK_N, int CL>
+template <int BLOCK_N, int CL, bool WRES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_x2,
@@ -98,6 +103,15 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     // ===================== TMA producer =====================
     if (lane == 0) {
       int slot = 0; uint32_t sphase = 0; int stage = 0; uint32_t bphase = 0;
+      if constexpr (WRES) {                                            // the whole filter bank, once: box (kc, tap) at index kc * 9 + tap
+        ptx::mbar_expect_tx(&b_full[0], (uint32_t)(9 * a.k_chunks * stage_stride));
+        for (int kc = 0; kc < a.k_chunks; ++kc)
+          for (int tap = 0; tap < 9; ++tap) {
+            uint8_t* pb = sB + (kc * 9 + tap) * stage_stride;
+            ptx::tma_load_3d(pb, &tmap_w, &b_full[0], kc * 32, tap, 0);
+            if (split3) ptx::tma_load_3d(pb + kBBytes, &tmap_w2, &b_full[0], kc * 32, tap, 0);
+          }
+      }
       for (int it = 0; it < iters; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         // phantom tile (ragged last round of a cluster): image index N is out of range -> the halo is all hardware zero fill
@@ -111,7 +125,7 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
           ptx::tma_load_4d(pa, &tmap_x, &a_full[slot], kc * 32, x0, y0, img);
           if (split3) ptx::tma_load_4d(pa + kSlotBytes, &tmap_x2, &a_full[slot], kc * 32, x0, y0, img);
           if (++slot == a.nslots) { slot = 0; sphase ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < (WRES ? 0 : 9); ++tap) {
             ptx::mbar_wait(&b_empty[stage], bphase ^ 1);                  // this CTA is done with the stage: arm its barrier
             uint8_t* pb = sB + stage * stage_stride;
             ptx::mbar_expect_tx(&b_full[stage], (uint32_t)stage_stride);
@@ -136,6 +150,10 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     constexpr uint32_t idesc = ptx::make_idesc_tf32(128, BLOCK_N, 0, 0);
     int slot = 0; uint32_t sphase = 0; int stage = 0; uint32_t bphase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    if constexpr (WRES) {
+      if (lane == 0) { ptx::mbar_wait(&b_full[0], 0); ptx::tc_fence_after(); }       // resident weights have landed
+      __syncwarp();
+    }
     for (int it = 0; it < iters; ++it) {
       if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       __syncwarp();
@@ -150,11 +168,13 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         const uint32_t sa0 = ptx::smem_u32(sA + slot * slot_stride);
         for (int tap = 0; tap < 9; ++tap) {
           if (lane == 0) {
-            ptx::mbar_wait(&b_full[stage], bphase);
-            ptx::tc_fence_after();
+            if constexpr (!WRES) {
+              ptx::mbar_wait(&b_full[stage], bphase);
+              ptx::tc_fence_after();
+            }
             const int kh = tap / 3, kw = tap - kh * 3;
             const uint32_t sa = sa0 + (uint32_t)((kh * kHW + kw) * 128);          // shifted view of the halo tile
-            const uint32_t sb = ptx::smem_u32(sB + stage * stage_stride);
+            const uint32_t sb = ptx::smem_u32(sB + (WRES ? kc * 9 + tap : stage) * stage_stride);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, kHW * 128);   // 8-pixel groups one halo row apart
@@ -165,7 +185,7 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
                 ptx::mma_tf32(tmem_d, da, ptx::make_smem_desc_sw128(sb + kBBytes + kk * 32, 16, 1024), idesc, 1u);
               }
             }
-            ptx::mma_commit(&b_empty[stage]);
+            if constexpr (!WRES) ptx::mma_commit(&b_empty[stage]);
             if constexpr (CL > 1) ptx::mma_commit_mcast(&b_empty_all[stage], (uint16_t)1);   // ... and tell the leader
             if (tap == 8) {
               ptx::mma_commit(&a_empty[slot]);                                     // the halo slot is free after its nine taps
@@ -278,7 +298,8 @@ bool encode(CUtensorMap* m, int rank, const void* base, const cuuint64_t* dims, 
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct HaloPlan { int bn, k_chunks, nslots, nstages, smem; };
+struct HaloPlan { int bn, k_chunks, nslots, nstages, smem, wres; };
+int g_halo_wres = 1;
 
 // shared-memory budget: halo slots (one per channel chunk, x2 for split precision) + weight stages + 2 staging tiles + barriers
 bool make_plan(int Cin, int Cout, int passes, HaloPlan* p) {
@@ -289,6 +310,15 @@ bool make_plan(int Cin, int Cout, int passes, HaloPlan* p) {
   const int slot = kSlotBytes * parts, stage = p->bn * 128 * parts;
   const int fixed = 2 * kOutStageBytes + 1024 /*align*/ + 512 /*barriers*/ + 2 * p->bn * 4 + 512;
   const int avail = 232448 - fixed;
+  p->wres = 0;
+  if (g_halo_wres && avail - 9 * p->k_chunks * stage >= p->k_chunks * slot) {     // the filter bank fits beside one halo tile: keep it resident
+    int nslots = (avail - 9 * p->k_chunks * stage) / slot;
+    if (nslots > 2 * p->k_chunks) nslots = 2 * p->k_chunks;
+    if (nslots > kMaxSlots) nslots = kMaxSlots;
+    p->wres = 1; p->nslots = nslots; p->nstages = 9 * p->k_chunks;
+    p->smem = nslots * slot + p->nstages * stage + fixed;
+    return true;
+  }
   int nstages = 4;
   if (avail - nstages * stage < p->k_chunks * slot) nstages = 3;
   int nslots = (avail - nstages * stage) / slot;
@@ -302,12 +332,12 @@ bool make_plan(int Cin, int Cout, int passes, HaloPlan* p) {
   return nstages >= 3;
 }
 
-template <int BLOCK_N, int CL>
+template <int BLOCK_N, int CL, bool WRES>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx2, const CUtensorMap& tw2, const HaloArgs& a,
            int smem, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_sm100_kernel<BLOCK_N, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_sm100_kernel<BLOCK_N, CL, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) { set_error("skd_conv3x3_halo_sm100(attr)", e); return 0; }
     attr = true;
   }
@@ -324,16 +354,16 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
     static int max_clusters = 0;
     if (max_clusters == 0) {
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo_sm100_kernel<BLOCK_N, CL>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / CL; }
+      if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo_sm100_kernel<BLOCK_N, CL, WRES>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / CL; }
       max_clusters = n;
     }
     grid = max_clusters * CL;
     if (grid > (kNumSMs / CL) * CL) grid = (kNumSMs / CL) * CL;
     cfg.gridDim = dim3(grid);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_halo_sm100_kernel<BLOCK_N, CL>, tx, tw, ty, tx2, tw2, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_halo_sm100_kernel<BLOCK_N, CL, WRES>, tx, tw, ty, tx2, tw2, a);
     if (e != cudaSuccess) { set_error("skd_conv3x3_halo_sm100(cluster launch)", e); return 0; }
   } else {
-    conv3x3_halo_sm100_kernel<BLOCK_N, CL><<<grid, kThreads, smem, st>>>(tx, tw, ty, tx2, tw2, a);
+    conv3x3_halo_sm100_kernel<BLOCK_N, CL, WRES><<<grid, kThreads, smem, st>>>(tx, tw, ty, tx2, tw2, a);
   }
   return finish("skd_conv3x3_halo_sm100");
 }
@@ -341,7 +371,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
 }  // namespace
 
 namespace skd {
-int g_halo_cluster = 1;
+int g_halo_cluster = 0;            // weight multicast across clusters of 4: measured SLOWER (lock-step release through the leader); opt-in via skd_set_conv_halo(5)
 int g_conv_halo = 1;   // skd_set_conv_halo(0): every shape through the general implicit-GEMM kernel
 
 bool conv3x3_halo_supported(int Cin, int Cout, int passes) {
@@ -389,13 +419,15 @@ int conv3x3_halo_launch(int N, int H, int W, int Cin, int Cout, const float* x, 
   a.passes = passes; a.nslots = p.nslots; a.nstages = p.nstages;
   a.scale = scale; a.shift = shift; a.act = act; a.slope = slope; a.round_out = round_tf32;
   // clusters of 4 share every weight box through TMA multicast; a handful of tiles is not worth a cluster
+  if (p.wres) return p.bn == 128 ? launch<128, 1, true>(tx, tw, ty, tx2, tw2, a, p.smem, st) : launch<64, 1, true>(tx, tw, ty, tx2, tw2, a, p.smem, st);
   const bool mc = g_halo_cluster && a.m_tiles >= 2 * kNumSMs;
-  if (p.bn == 128) return mc ? launch<128, 4>(tx, tw, ty, tx2, tw2, a, p.smem, st) : launch<128, 1>(tx, tw, ty, tx2, tw2, a, p.smem, st);
-  return mc ? launch<64, 4>(tx, tw, ty, tx2, tw2, a, p.smem, st) : launch<64, 1>(tx, tw, ty, tx2, tw2, a, p.smem, st);
+  if (p.bn == 128) return mc ? launch<128, 4, false>(tx, tw, ty, tx2, tw2, a, p.smem, st) : launch<128, 1, false>(tx, tw, ty, tx2, tw2, a, p.smem, st);
+  return mc ? launch<64, 4, false>(tx, tw, ty, tx2, tw2, a, p.smem, st) : launch<64, 1, false>(tx, tw, ty, tx2, tw2, a, p.smem, st);
 }
 }  // namespace skd
 
-extern "C" void skd_set_conv_halo(int on) { skd::g_conv_halo = (on & 1) ? 1 : 0; skd::g_halo_cluster = (on & 2) ? 0 : 1; }   // bit 1: no weight multicast
+// bit 0: halo kernel on; bit 1: NO resident weights (always the streaming ring); bit 2: weight multicast over clusters of 4
+extern "C" void skd_set_conv_halo(int on) { skd::g_conv_halo = (on & 1) ? 1 : 0; g_halo_wres = (on & 2) ? 0 : 1; skd::g_halo_cluster = (on & 4) ? 1 : 0; }
 
 extern "C" int skd_conv3x3_halo_sm100(int N, int H, int W, int Cin, int Cout, const float* x, const float* x_lo, int ldx, const float* w,
                                       const float* w_lo, float* y, int ldy, const float* scale, const float* shift, int act, float slope,

@@ -31,22 +31,26 @@ struct WgArgs {
   int linear;                              // K-blocks are 32 consecutive output pixels (dY as a [P][Cout] matrix, X through TMA im2col)
 };
 
-template <int BLOCK_N>
+// PAIR = 2: a cluster of two CTAs (cta_group::2) owns a 256 (Cout) x BLOCK_N (Cin) tile: each CTA stages its own 128 Cout rows of dY
+// and only HALF of the x tile (BLOCK_N / 2 channels), the leader issues M = 256 MMAs.  Per 128 x BLOCK_N of MMA work a CTA then moves
+// 8 TMA boxes instead of 12 (BLOCK_N = 256) -- the producer's box rate, not the tensor pipe, bounded the single-CTA kernel (ncu:
+// tensor pipe 59 % of active cycles on 512 -> 512) -- and the freed shared memory gives a third pipeline stage.
+template <int BLOCK_N, int PAIR = 1>
 struct WCfg {
   static constexpr int kKPix = kpix_for(BLOCK_N);
   static constexpr int kChunkBytes = 32 * kKPix * 4;                 // one 32-channel x kKPix-pixel box
   static constexpr int kABytes = 4 * kChunkBytes;                    // 128 co
-  static constexpr int kBBytes = (BLOCK_N / 32) * kChunkBytes;
+  static constexpr int kBBytes = (BLOCK_N / 32 / PAIR) * kChunkBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 2);
+  static constexpr int kStages = (PAIR == 2) ? 3 : ((BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 2));
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgArgs a) {
-  using C = WCfg<BLOCK_N>;
+  using C = WCfg<BLOCK_N, PAIR>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the pointer in the shared address space (integer round trips make nvcc emit generic LD/ST instead of LDS/STS)
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -57,20 +61,27 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (PAIR == 2) ? ptx::cluster_ctarank() : 0u;
+  const int unit0 = (PAIR == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = (PAIR == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_dy); ptx::prefetch_tmap(&tmap_x);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4 * PAIR); }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  if (warp == 1) {
+    if constexpr (PAIR == 2) ptx::tmem_alloc_2cta<C::kTmemCols>(tmem_base_slot);
+    else ptx::tmem_alloc<C::kTmemCols>(tmem_base_slot);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  const int tiles = a.m_tiles * a.taps * a.n_tiles;
+  const int m_units = a.m_tiles / PAIR;                    // pair mode: a tile is two consecutive 128-row Cout tiles (Cout % 256 == 0)
+  const int tiles = m_units * a.taps * a.n_tiles;
   const int units = tiles * a.splits;
   const int kb_per_img = a.kb_x * a.kb_y;
 
@@ -80,19 +91,42 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
     // swizzle allows (32 channels x 64 pixels = 8 KB) and all-out-of-range channel chunks (Cout or Cin < tile) are not issued.
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const uint32_t full_bar0 = (PAIR == 2) ? ptx::mapa_shared(&full_bar[0], 0) : 0u;   // the leader's full barriers
+      for (int u = unit0; u < units; u += unit_step) {
         const int split = u / tiles, tile = u - split * tiles;
-        const int mt = tile / (a.taps * a.n_tiles), r = tile - mt * (a.taps * a.n_tiles);
+        const int mu = tile / (a.taps * a.n_tiles), r = tile - mu * (a.taps * a.n_tiles);
+        const int mt = (PAIR == 2) ? 2 * mu + (int)cta_rank : mu;
         const int tap = r / a.n_tiles, nt = r - tap * a.n_tiles;
         const int kh = tap / a.KW, kw = tap - kh * a.KW;
         const int kb0 = split * a.kb_per_split;
         const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
         const int a_chunks = min(4, (a.Cout - mt * kBlockM + 31) / 32);
-        const int b_chunks = min(BLOCK_N / 32, (a.Cin - nt * BLOCK_N + 31) / 32);
+        // pair mode: this CTA stages channels [nt * BLOCK_N + rank * BLOCK_N / 2, +BLOCK_N / 2) of x
+        const int n0 = nt * BLOCK_N + (int)cta_rank * (BLOCK_N / PAIR);
+        const int b_chunks = max(0, min(BLOCK_N / 32 / PAIR, (a.Cin - n0 + 31) / 32));
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
+          if constexpr (PAIR == 2) {
+            // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both (the peer's chunk counts are its own:
+            // Cout % 256 == 0 makes a_chunks 4 in both; the peer's share of x may be ragged)
+            if (cta_rank == 0) {
+              const int peer_b = max(0, min(BLOCK_N / 64, (a.Cin - (nt * BLOCK_N + BLOCK_N / 2) + 31) / 32));
+              ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)((2 * a_chunks + b_chunks + peer_b) * C::kChunkBytes));
+            }
+            const uint32_t fb = full_bar0 + (uint32_t)stage * 8u;
+            const int p0 = kb * C::kKPix;
+            const int img = p0 / (a.OH * a.OW), r2 = p0 - img * (a.OH * a.OW);
+            const int oy = r2 / a.OW, ox = r2 - oy * a.OW;
+            for (int c = 0; c < a_chunks; ++c)
+              ptx::tma_load_4d_2cta(sa + c * C::kChunkBytes, &tmap_dy, fb, mt * kBlockM + c * 32, p0, 0, 0);
+            for (int c = 0; c < b_chunks; ++c)
+              ptx::tma_load_im2col_4d_2cta(sb + c * C::kChunkBytes, &tmap_x, fb, n0 + c * 32, ox * a.stride - a.pad, oy * a.stride - a.pad, img,
+                                           (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)((a_chunks + b_chunks) * C::kChunkBytes));
           if (a.linear) {
             const int p0 = kb * C::kKPix;
@@ -118,9 +152,9 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, BLOCK_N, 1, 1);     // both operands MN-major
+    constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM * PAIR, BLOCK_N, 1, 1);     // both operands MN-major
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = unit0; u < units && cta_rank == 0; u += unit_step) {
       const int split = u / tiles, tile = u - split * tiles;
       const int kb0 = split * a.kb_per_split;
       const int nkb = min(a.kb_total, kb0 + a.kb_per_split) - kb0;
@@ -140,10 +174,16 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
             // LBO = distance between 32-channel chunks, SBO = distance between 4-pixel groups
             const uint64_t da = ptx::make_smem_desc(sa + kk * 1024, C::kChunkBytes, 512, 1);   // 8 pixels = 1 KB per MMA K step
             const uint64_t db = ptx::make_smem_desc(sb + kk * 1024, C::kChunkBytes, 512, 1);
-            ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+            if constexpr (PAIR == 2) ptx::mma_tf32_2cta(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+            else ptx::mma_tf32(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
           }
-          ptx::mma_commit(&empty_bar[stage]);
-          if (k == nkb - 1) ptx::mma_commit(&tmem_full[acc]);
+          if constexpr (PAIR == 2) {
+            ptx::mma_commit_2cta(&empty_bar[stage]);
+            if (k == nkb - 1) ptx::mma_commit_2cta(&tmem_full[acc]);
+          } else {
+            ptx::mma_commit(&empty_bar[stage]);
+            if (k == nkb - 1) ptx::mma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -155,9 +195,11 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
     const int row = quarter * 32 + lane;
     const size_t kdim = (size_t)a.taps * a.Cin;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const uint32_t tmem_empty0 = (PAIR == 2) ? ptx::mapa_shared(&tmem_empty[0], 0) : 0u;   // the leader's tmem_empty barriers
+    for (int u = unit0; u < units; u += unit_step) {
       const int split = u / tiles, tile = u - split * tiles;
-      const int mt = tile / (a.taps * a.n_tiles), r = tile - mt * (a.taps * a.n_tiles);
+      const int mu = tile / (a.taps * a.n_tiles), r = tile - mu * (a.taps * a.n_tiles);
+      const int mt = (PAIR == 2) ? 2 * mu + (int)cta_rank : mu;
       const int tap = r / a.n_tiles, nt = r - tap * a.n_tiles;
       const int co = mt * kBlockM + row;
       float* orow = a.ws + ((size_t)split * a.Cout + co) * kdim + (size_t)tap * a.Cin;
@@ -186,13 +228,20 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR == 2) ptx::mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
+        else ptx::mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc<C::kTmemCols>(tmem_base); }
+  if constexpr (PAIR == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (PAIR == 2) ptx::tmem_dealloc_2cta<C::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -220,9 +269,10 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-struct Plan { int OH, OW, BHk, BWk, kb_x, kb_y, kb_total, bn, m_tiles, n_tiles, taps, splits, kb_per_split, linear; };
+struct Plan { int OH, OW, BHk, BWk, kb_x, kb_y, kb_total, bn, m_tiles, n_tiles, taps, splits, kb_per_split, linear, pair; };
 
 int g_wgrad_linear = 1;
+int g_wgrad_pairs = 1;            // cta_group::2 pairs for 256-wide Cin tiles with Cout % 256 == 0
 
 Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil) {
   Plan p;
@@ -249,20 +299,22 @@ Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int strid
   p.linear = g_wgrad_linear && pad <= 128 && up_h >= -128 && up_w >= -128 && stride <= 8 && (long long)N * p.OH * p.OW < (1LL << 31);
   if (p.linear) p.kb_total = (int)(((long long)N * p.OH * p.OW + kpix - 1) / kpix);
   p.m_tiles = (Cout + kBlockM - 1) / kBlockM; p.n_tiles = (Cin + p.bn - 1) / p.bn; p.taps = KH * KW;
-  const int tiles = p.m_tiles * p.n_tiles * p.taps;
+  p.pair = (g_wgrad_pairs && p.linear && p.bn == 256 && Cout % 256 == 0) ? 1 : 0;
+  const int tiles = (p.m_tiles / (p.pair ? 2 : 1)) * p.n_tiles * p.taps;
+  const int slots = p.pair ? kNumSMs / 2 : kNumSMs;          // persistent CTAs (or CTA pairs)
   // split-K: work units = tiles x K ranges over a persistent grid of kNumSMs CTAs.  Pick the split count whose unit count fills
   // whole waves best (ncu, round 2: 9 tiles x 33 splits = 297 units = 2 waves + ONE unit -> a third round, 34 % of the SM cycles
   // idle; 72 tiles x 5 = 360 units = 2.4 waves -> 23 % idle), fewer splits on ties (each split writes a partial dW plane)
   int cap = p.kb_total / 16; if (cap < 1) cap = 1;          // at least 16 k-blocks per unit
-  int hi = (4 * kNumSMs + tiles - 1) / tiles; if (hi > cap) hi = cap; if (hi < 1) hi = 1;
+  int hi = (4 * slots + tiles - 1) / tiles; if (hi > cap) hi = cap; if (hi < 1) hi = 1;
   int best_sp = 1; double best_eff = -1.0;
   for (int sp = 1; sp <= hi; ++sp) {
     const int kps = (p.kb_total + sp - 1) / sp;
     const int real = (p.kb_total + kps - 1) / kps;             // splits that actually get work
     const long long units = (long long)tiles * real;
-    const long long waves = (units + kNumSMs - 1) / kNumSMs;
-    double eff = (double)units / (double)(waves * kNumSMs);
-    if (units < kNumSMs) eff = (double)units / kNumSMs * 0.999;   // less than one wave: more units is better
+    const long long waves = (units + slots - 1) / slots;
+    double eff = (double)units / (double)(waves * slots);
+    if (units < slots) eff = (double)units / slots * 0.999;       // less than one wave: more units is better
     if (eff > best_eff + 0.02) { best_eff = eff; best_sp = real; }
   }
   int splits = best_sp;
@@ -271,23 +323,36 @@ Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int strid
   return p;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int PAIR>
 int launch(const CUtensorMap& tdy, const CUtensorMap& tx, const WgArgs& a, int units, cudaStream_t st) {
-  using C = WCfg<BLOCK_N>;
+  using C = WCfg<BLOCK_N, PAIR>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_sm100_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_sm100_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("skd_conv2d_wgrad_sm100(attr)", e); return 0; }
     attr = true;
   }
-  const int grid = units < kNumSMs ? units : kNumSMs;
-  conv_wgrad_sm100_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(tdy, tx, a);
+  if constexpr (PAIR == 2) {
+    int pairs = units < kNumSMs / 2 ? units : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_wgrad_sm100_kernel<BLOCK_N, PAIR>, tdy, tx, a);
+    if (e != cudaSuccess) { set_error("skd_conv2d_wgrad_sm100(pair launch)", e); return 0; }
+  } else {
+    const int grid = units < kNumSMs ? units : kNumSMs;
+    conv_wgrad_sm100_kernel<BLOCK_N, PAIR><<<grid, kThreads, C::kSmemBytes, st>>>(tdy, tx, a);
+  }
   return finish("skd_conv2d_wgrad_sm100");
 }
 
 }  // namespace
 
 extern "C" void skd_set_wgrad_linear(int on) { g_wgrad_linear = on ? 1 : 0; }
+extern "C" void skd_set_wgrad_cta_pairs(int on) { g_wgrad_pairs = on ? 1 : 0; }
 
 extern "C" long long skd_conv2d_wgrad_sm100_workspace_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
                                                              int pad, int dil) {
@@ -368,13 +433,13 @@ extern "C" int skd_conv2d_wgrad_sm100(int N, int H, int W, int Cin, int Cout, in
   a.splits = p.splits; a.kb_total = p.kb_total; a.kb_per_split = p.kb_per_split;
   a.ws = p.splits == 1 ? dw : workspace;
   a.linear = p.linear;
-  const int units = p.m_tiles * p.n_tiles * p.taps * p.splits;
+  const int units = (p.m_tiles / (p.pair ? 2 : 1)) * p.n_tiles * p.taps * p.splits;
   int ok;
   switch (p.bn) {
-    case 256: ok = launch<256>(tdy, tx, a, units, st); break;
-    case 128: ok = launch<128>(tdy, tx, a, units, st); break;
-    case 64: ok = launch<64>(tdy, tx, a, units, st); break;
-    default: ok = launch<32>(tdy, tx, a, units, st); break;
+    case 256: ok = p.pair ? launch<256, 2>(tdy, tx, a, units, st) : launch<256, 1>(tdy, tx, a, units, st); break;
+    case 128: ok = launch<128, 1>(tdy, tx, a, units, st); break;
+    case 64: ok = launch<64, 1>(tdy, tx, a, units, st); break;
+    default: ok = launch<32, 1>(tdy, tx, a, units, st); break;
   }
   if (!ok) return 0;
   if (p.splits > 1) {

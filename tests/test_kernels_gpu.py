@@ -477,6 +477,26 @@ def test_conv3x3_halo_kernel(ops, case):
     assert not torch.isnan(y).any()
     e = rel(y.permute(0, 3, 1, 2), ref)
     assert e < (2e-5 if precise else 2e-3), e
+    # streaming weight ring instead of the resident filter bank (the default where it fits): same MMAs in the same order
+    ys = torch.full((N, H, W, Cout), float("nan"), device="cuda")
+    try:
+        L.skd_set_conv_halo(3)
+        L.skd_conv3x3_halo_sm100(N, H, W, Cin, Cout, x.data_ptr(), x_lo.data_ptr() if precise else None, Cin, w.data_ptr(),
+                                 w_lo.data_ptr() if precise else None, ys.data_ptr(), Cout, scale.data_ptr(), shift.data_ptr(), 3, 0.0, _st())
+        torch.cuda.synchronize()
+    finally:
+        L.skd_set_conv_halo(1)
+    assert torch.equal(ys, y)
+    if N * ((H + 15) // 16) * ((W + 7) // 8) >= 296:               # enough tiles for the cluster variant: multicast weights, phantom tiles
+        ym = torch.full((N, H, W, Cout), float("nan"), device="cuda")
+        try:
+            L.skd_set_conv_halo(5)
+            L.skd_conv3x3_halo_sm100(N, H, W, Cin, Cout, x.data_ptr(), x_lo.data_ptr() if precise else None, Cin, w.data_ptr(),
+                                     w_lo.data_ptr() if precise else None, ym.data_ptr(), Cout, scale.data_ptr(), shift.data_ptr(), 3, 0.0, _st())
+            torch.cuda.synchronize()
+        finally:
+            L.skd_set_conv_halo(1)
+        assert torch.equal(ym, y)
     if not precise:
         try:
             L.skd_set_conv_halo(1)
@@ -484,9 +504,36 @@ def test_conv3x3_halo_kernel(ops, case):
             L.skd_set_conv_halo(0)
             y3 = ops.conv2d_fwd(x.permute(0, 3, 1, 2), w, 1, 1, 1, scale=scale, shift=shift, act="relu")
         finally:
-            L.skd_set_conv_halo(0)
+            L.skd_set_conv_halo(1)
         assert torch.equal(y2.permute(0, 2, 3, 1), y)
         assert rel(y3, y2) < 1e-3                                  # the general kernel: same TF32 products, another summation order
+
+
+@pytest.mark.parametrize("case", [(2, 512, 33, 31, 512, 3, 1, 4, 4), (1, 256, 65, 129, 256, 3, 1, 2, 2), (2, 260, 20, 17, 512, 1, 1, 0, 1),
+                                  (1, 1024, 9, 11, 256, 3, 1, 1, 1), (2, 256, 33, 31, 512, 3, 2, 1, 1)])
+def test_conv_wgrad_cta_pairs(ops, case):
+    """conv_wgrad_sm100_kernel<256, 2>: cta_group::2 pairs own 256 (Cout) x 256 (Cin) tiles, each CTA staging its 128 Cout rows of dY and
+    half of the x tile (MN-major operands, 2-CTA TMA loads, multicast commits).  Same products in the same order as the single-CTA
+    kernel: identical results, and both within TF32 tolerance of float64."""
+    from structure_knowledge_distillation_b200._cabi import lib
+    N, Cin, H, W, Cout, k, s, p, d = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case) + 11)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).double()
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).double().requires_grad_(True)
+    y = F.conv2d(x, w, None, s, p, d)
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(dy.double())
+    xc = ops.to_nhwc(x.float()); dyc = ops.to_nhwc(dy)
+    dw_ref = w.grad.permute(0, 2, 3, 1)
+    try:
+        lib().skd_set_wgrad_cta_pairs(1)
+        a = ops.conv2d_wgrad(xc, dyc, (k, k), s, p, d)
+        lib().skd_set_wgrad_cta_pairs(0)
+        b = ops.conv2d_wgrad(xc, dyc, (k, k), s, p, d)
+    finally:
+        lib().skd_set_wgrad_cta_pairs(1)
+    assert rel(a, dw_ref) < 2e-3 and rel(b, dw_ref) < 2e-3, (rel(a, dw_ref), rel(b, dw_ref))
+    assert rel(a, b) < 1e-5, rel(a, b)
 
 
 @pytest.mark.parametrize("case", [(1, 256, 8, 8, 512, 4, 2, 1, 1), (2, 256, 8, 8, 512, 4, 2, 1, 1), (1, 128, 16, 16, 256, 4, 2, 1, 1),

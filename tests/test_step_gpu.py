@@ -15,7 +15,7 @@ def _build(name):
     from oracle import cases, port
     from structure_knowledge_distillation_b200.networks.kd_model import NetModel
     from structure_knowledge_distillation_b200.utils.train_options import make_args
-    spec = cases.STEP_CASES.get(name) or cases.FULL_CASES[name]
+    spec = cases.STEP_CASES.get(name) or cases.CFG4_CASES.get(name) or cases.FULL_CASES[name]
     cfg = port.StepConfig(**spec["cfg"])
     teacher, student, D = cases.build_models(seed=0, with_D=True)
     if not cfg.ho:
@@ -45,9 +45,9 @@ def _relerr(a, b):
 
 
 @pytest.mark.parametrize("name", ["cfg1_pi_64", "pi_pa_96x128", "pi_pa_ho_hinge_512", "pi_pa_ho_wgangp_512",
-                                  "baseline_cfg3_b8_512x1024"])
+                                  "cfg4_pi_pa_360x480_b2", "baseline_cfg3_b8_512x1024"])
 def test_distillation_step_matches_reference_golden(name):
-    fname = "steps_full.pt" if name.startswith("baseline") else "steps.pt"
+    fname = "steps_full.pt" if name.startswith("baseline") else ("steps_cfg4.pt" if name.startswith("cfg4") else "steps.pt")
     gold = torch.load(os.path.join(ROOT, "tests", "golden", fname), weights_only=False)[name]
     m, cfg = _build(name)
     m.forward()
@@ -93,33 +93,7 @@ def test_distillation_step_matches_reference_golden(name):
         # (1) the discriminator phase ON IDENTICAL INPUTS: oracle/port.py in float64 (autograd, double backward for the penalty) fed
         # with OUR teacher / student logits and the same D state -- isolates this phase from the student's TF32 logit perturbation,
         # to which the golden's D gradients are very sensitive on the batch-1 cases (one 4x4 map at the top of D)
-        from oracle import port
-        Dq = port.Discriminator(1, 19, 64)
-        Dq.load_state_dict({k: v.cpu() for k, v in d_state.items()})
-        Dq = Dq.cuda().double().train()
-        tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
-        try:
-            ls, lt = m.preds_S[0].detach().double().contiguous(), m.preds_T[0].detach().double().contiguous()
-            dT, dS = Dq(lt), Dq(ls)                                                     # kd_model.py:156-157 order
-            dl = cfg.lambda_d * port.adv_loss_d(dS, dT, cfg.adv_type)
-            if cfg.adv_type == "wgan-gp":
-                dl = dl + cfg.lambda_d * port.gradient_penalty(Dq, ls, lt, m.criterion_AdditionalGP.alpha.double(), cfg.lambda_gp)
-            dl.backward()
-        finally:
-            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
-        report["D_same_inputs"] = _relerr(m.D_loss, dl)
-        refs = dict(Dq.named_parameters())
-        topq = max(float(q.grad.norm()) for q in refs.values() if q.grad is not None)
-        wq, wqn = 0.0, None
-        for pname, p in m.D_model.named_parameters():
-            q = refs.get(pname)
-            if q is None or q.grad is None or p.grad is None:
-                continue
-            e = float((p.grad.detach().double() - q.grad).norm() / max(float(q.grad.norm()), 1e-3 * topq))
-            if e > wq:
-                wq, wqn = e, pname
-        report["worst_D_grad_rel_l2_same_inputs"] = (wq, wqn)
+        report["D_same_inputs"], report["worst_D_grad_rel_l2_same_inputs"] = _d_phase_vs_port(m, cfg, d_state)
         # per-tensor comparison.  Gradients that cancel analytically (attention gammas at their zero init: <gy, O> summed over
         # positions of both signs; last.0.bias: +mean - mean) are round-off residue 3-4 orders below the other tensors in the
         # reference's own fp32 run, so every denominator is floored at 1e-3 of the largest gradient norm of the step
@@ -171,6 +145,75 @@ def test_distillation_step_matches_reference_golden(name):
         assert report["worst_D_grad_norm_rel"][0] < (0.05 if full else 0.3), report["worst_D_grad_norm_rel"]
         if full:
             assert report["worst_D_grad_samples_rel_l2"][0] < 0.1, report["worst_D_grad_samples_rel_l2"]
+
+
+def _d_phase_vs_port(m, cfg, d_state):
+    """The discriminator phase that just ran in `m` against oracle/port.py in float64 (autograd, double backward for the penalty)
+    fed with OUR teacher / student logits and the D state from before the phase.  -> (loss rel. error, (worst grad rel-L2, name))"""
+    import torch.nn.functional as F
+    from oracle import port
+    Dq = port.Discriminator(1, 19, 64)
+    Dq.load_state_dict({k: v.cpu() for k, v in d_state.items()})
+    Dq = Dq.cuda().double().train()
+    hc, wc = m.preds_S[0].shape[2:]
+    for _ in range(4):
+        hc, wc = (hc - 2) // 2 + 1, (wc - 2) // 2 + 1
+    last = Dq.last[0]
+    if hc < 4 or wc < 4:                                   # logits smaller than 64 pixels (360x480 crops): the same size-aware head as ours
+        class _Head(torch.nn.Module):
+            def forward(self, x):
+                return F.conv2d(x, last.weight[:, :, :min(4, hc), :min(4, wc)], last.bias)
+        Dq.last_conv = last
+        Dq.last = torch.nn.Sequential(_Head())
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ls, lt = m.preds_S[0].detach().double().contiguous(), m.preds_T[0].detach().double().contiguous()
+        dT, dS = Dq(lt), Dq(ls)                                                     # kd_model.py:156-157 order
+        dl = cfg.lambda_d * port.adv_loss_d(dS, dT, cfg.adv_type)
+        if cfg.adv_type == "wgan-gp":
+            dl = dl + cfg.lambda_d * port.gradient_penalty(Dq, ls, lt, m.criterion_AdditionalGP.alpha.double(), cfg.lambda_gp)
+        dl.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    refs = dict(Dq.named_parameters())
+    if hasattr(Dq, "last_conv"):
+        refs["last.0.weight"], refs["last.0.bias"] = Dq.last_conv.weight, Dq.last_conv.bias
+    topq = max(float(q.grad.norm()) for q in refs.values() if q.grad is not None)
+    wq, wqn = 0.0, None
+    for pname, p in m.D_model.named_parameters():
+        q = refs.get(pname)
+        if q is None or q.grad is None or p.grad is None:
+            continue
+        e = float((p.grad.detach().double() - q.grad).norm() / max(float(q.grad.norm()), 1e-3 * topq))
+        if e > wq:
+            wq, wqn = e, pname
+    return _relerr(m.D_loss, dl), (wq, wqn)
+
+
+def test_config4_shape_holistic_step():
+    """BASELINE.json configs[3] shape with the holistic loss: 360x480 crops -> 46x61 logits -> a 2x3 map under D's 4x4 'last' conv,
+    where the reference's own discriminator cannot run (sagan_models.py:131-136,163).  One full step (Pi+Pa+Ho wgan-gp) through
+    NetModel; the discriminator phase is checked against oracle/port.py with the same size-aware head on identical logits."""
+    from oracle import cases, port
+    from structure_knowledge_distillation_b200.networks.kd_model import NetModel
+    from structure_knowledge_distillation_b200.utils.train_options import make_args
+    cfg = port.StepConfig(pi=True, pa=True, ho=True, adv_type="wgan-gp")
+    teacher, student, D = cases.build_models(seed=0, with_D=True)
+    m = NetModel(make_args(batch_size=2, pi=True, pa=True, ho=True, adv_loss_type="wgan-gp"))
+    m.student.load_state_dict(student.state_dict()); m.teacher.load_state_dict(teacher.state_dict()); m.D_model.load_state_dict(D.state_dict())
+    images, labels = port.synthetic_batch(2, 360, 480, seed=1)
+    m.criterion_AdditionalGP.alpha = torch.rand(2, 1, 1, 1, generator=cases.seeded(3)).cuda()
+    m.set_input((images, labels, None, None))
+    m.forward(); m.G_solver.zero_grad(); m.student_backward(); m.G_solver.step()
+    assert tuple(m.preds_S[0].shape[2:]) == (46, 61)
+    d_state = {k: v.detach().clone() for k, v in m.D_model.state_dict().items()}
+    m.discriminator_backward()
+    e_loss, worst = _d_phase_vs_port(m, cfg, d_state)
+    print("\nPARITY config4_ho_360x480 D loss %.2e worst D grad rel-L2 (identical inputs) %.2e (%s) G %.4f" % (e_loss, worst[0], worst[1], float(m.G_loss)))
+    assert e_loss < 1e-4 and worst[0] < 3e-2
+    for v in (m.G_loss, m.D_loss, m.pi_G_loss, m.pa_G_loss):
+        assert float(v) == float(v)                                            # finite
 
 
 def _snapshot(m):
