@@ -92,6 +92,15 @@ int skd_dsn_ce_bwd(int N, int C, int h, int w, int H, int W, const float* L0, lo
                    const float* L1, long long b_sn, long long b_sc, long long b_sp, const long long* labels, int ignore_index,
                    float w0, float w1, const float* grad_out, const float* count, float* d0, float* d1, float* workspace,
                    cudaStream_t);
+/* training forward = loss + count + the backward's row phase in ONE pass over the upsampled pixels (one softmax per pixel and step
+   instead of two); skd_dsn_ce_bwd_cols finishes the backward from `rows_ws` (skd_dsn_ce_bwd_workspace_floats floats) */
+long long skd_dsn_ce_train_partials(int N, int H, int heads);       /* doubles */
+int skd_dsn_ce_fwd_train(int N, int C, int h, int w, int H, int W, const float* logits0, long long a_sn, long long a_sc, long long a_sp,
+                         const float* logits1, long long b_sn, long long b_sc, long long b_sp, const long long* labels, int ignore_index,
+                         float w0, float w1, float* loss, float* count, double* partials, float* rows_ws, cudaStream_t);
+int skd_dsn_ce_bwd_cols(int N, int C, int h, int w, int H, const float* rows_ws, long long a_sn, long long a_sc, long long a_sp,
+                        long long b_sn, long long b_sc, long long b_sp, int heads, float w0, float w1, const float* grad_out,
+                        const float* count, float* d0, float* d1, cudaStream_t);
 /* CriterionPairWiseforWholeFeatAfterPool.forward (utils/criterion.py:236-245) + sim_dis_compute (utils/utils.py:170-183):
    pool: ceil-mode max pool kernel=stride=(ph,pw) -> pooled[N][nodes][C], argmax (pixel index, may be NULL), rnorm[N][nodes] */
 int skd_pairwise_pool(int N, int C, int H, int W, const float* F, long long sn, long long sc, long long sp, int ph, int pw,

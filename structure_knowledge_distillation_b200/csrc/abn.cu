@@ -328,16 +328,15 @@ __global__ void nhwc_stats_finalize_kernel(const float* __restrict__ x, const fl
                                            float* running_mean, float* running_var, float* __restrict__ mean,
                                            float* __restrict__ var, float* __restrict__ scale,
                                            float* __restrict__ shift) {
-  // 32 channels x 16 row-lanes per block: the R split partials of a channel are summed by 16 threads, then by lane 0
-  __shared__ float sh1[16][33], sh2[16][33];
-  const int cx = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  // one WARP per channel (8 channels per block): the R (~600) split partials of a channel are read by 32 lanes -- ~19 dependent loads
+  // per thread instead of 37 -- and folded with shuffles (ncu, round 2: the 2-block version took 10-12 us per layer, 58 times a step)
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
   float s1 = 0.f, s2 = 0.f;
-  if (c < C) for (int r = lane; r < R; r += 16) { float2 p = partial[(size_t)r * C + c]; s1 += p.x; s2 += p.y; }
-  sh1[lane][cx] = s1; sh2[lane][cx] = s2;
-  __syncthreads();
-  if (lane != 0 || c >= C) return;
-  for (int k = 1; k < 16; ++k) { s1 += sh1[k][cx]; s2 += sh2[k][cx]; }
+  for (int r = lane; r < R; r += 32) { float2 p = partial[(size_t)r * C + c]; s1 += p.x; s2 += p.y; }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane != 0) return;
   const float K = x[c];
   const float m = s1 / count;
   const float mu = K + m;
@@ -463,16 +462,14 @@ __global__ void nhwc_bwd_finalize_kernel(const float2* __restrict__ partial, int
                                          const float* __restrict__ weight, float* __restrict__ edz,
                                          float* __restrict__ eydz, float* __restrict__ dweight,
                                          float* __restrict__ dbias) {
-  // 32 channels x 16 row-lanes per block: the R split partials of a channel are summed by 16 threads, then by lane 0
-  __shared__ float sh1[16][33], sh2[16][33];
-  const int cx = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  // one warp per channel, 8 channels per block (see nhwc_stats_finalize_kernel)
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
   float s1 = 0.f, s2 = 0.f;
-  if (c < C) for (int r = lane; r < R; r += 16) { float2 p = partial[(size_t)r * C + c]; s1 += p.x; s2 += p.y; }
-  sh1[lane][cx] = s1; sh2[lane][cx] = s2;
-  __syncthreads();
-  if (lane != 0 || c >= C) return;
-  for (int k = 1; k < 16; ++k) { s1 += sh1[k][cx]; s2 += sh2[k][cx]; }
+  for (int r = lane; r < R; r += 32) { float2 p = partial[(size_t)r * C + c]; s1 += p.x; s2 += p.y; }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane != 0) return;
   edz[c] = s1 / count; eydz[c] = s2 / count;
   if (dweight) { const float w = weight[c]; dweight[c] = w > 0.f ? s2 : (w < 0.f ? -s2 : 0.f); }   // bn.cu:217-223
   if (dbias) dbias[c] = s1;
@@ -618,7 +615,7 @@ extern "C" int skd_abn_stats_nhwc(long long P, int C, const float* x, const floa
   if (P <= 0) return 1;
   const int chunks = (C / 4 + 255) / 256;
   nhwc_stats_partial_kernel<<<dim3(splits, chunks), 256, 0, st>>>(x, reinterpret_cast<float2*>(workspace), P, C);
-  nhwc_stats_finalize_kernel<<<(C + 31) / 32, 512, 0, st>>>(x, reinterpret_cast<const float2*>(workspace), splits, C,
+  nhwc_stats_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(x, reinterpret_cast<const float2*>(workspace), splits, C,
                                                              (float)P, weight, bias, eps, momentum, running_mean,
                                                              running_var, mean, var, scale, shift);
   return finish("skd_abn_stats_nhwc", 2);
@@ -653,7 +650,7 @@ extern "C" int skd_abn_bwd_reduce_nhwc(long long P, int C, int S, const float* x
   const int chunks = (C / 4 + 255) / 256;
   nhwc_bwd_partial_kernel<<<dim3(splits, chunks), 256, 0, st>>>(x, out, dout, reinterpret_cast<float2*>(workspace), P, C, S,
                                                                mean, var, eps, act, slope, chan_mul, scale, shift);
-  nhwc_bwd_finalize_kernel<<<(C + 31) / 32, 512, 0, st>>>(reinterpret_cast<const float2*>(workspace), splits, C, (float)P,
+  nhwc_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(reinterpret_cast<const float2*>(workspace), splits, C, (float)P,
                                                            weight, edz, eydz, dweight, dbias);
   return finish("skd_abn_bwd_reduce_nhwc", 2);
 }

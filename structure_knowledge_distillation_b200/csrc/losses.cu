@@ -177,10 +177,16 @@ dsn_ce_fwd_kernel(const float* __restrict__ L0, const float* __restrict__ L1, St
 // The X that feed source column x are contiguous runs (i0 is monotonic in X): those with i0 == x (weight wa = l0, plus l1 where
 // the right neighbour is clamped onto the same column) and those with i0 == x-1 (weight wb = l1).  The run starts first[x] are
 // found once per chunk, so a (x, c) pair is ~2*W/w shared-memory FMAs.  Lanes run over c (odd row pitch: conflict-free).
+// LOSS = true: the same pass also produces the loss (it has every pixel's log-sum-exp in hand): the training forward then IS the
+// backward's first phase, and the backward proper is only phase 2 -- one softmax over the 2 x 8 x 512 x 1024 upsampled pixels per
+// step instead of two (skd_dsn_ce_fwd_train / skd_dsn_ce_bwd_cols).
+template <bool LOSS>
 __global__ void __launch_bounds__(1024)
 dsn_ce_bwd_rows_kernel(const float* __restrict__ L0, const float* __restrict__ L1, Strides s0, Strides s1,
                        const long long* __restrict__ labels, int N, int C, int h, int w, int H, int W, int ignore,
-                       float* __restrict__ T1, int chunk) {
+                       float* __restrict__ T1, int chunk, double* __restrict__ part_loss, double* __restrict__ part_cnt, float w0, float w1) {
+  __shared__ double shd[32];
+  double loss_acc = 0.0, cnt_acc = 0.0;
   extern __shared__ float G[];                                 // [C][chunk|1], wa[chunk], wb[chunk], first[w+1]
   const int pitch = chunk | 1;
   float* wa = G + (size_t)C * pitch;
@@ -211,8 +217,13 @@ dsn_ce_bwd_rows_kernel(const float* __restrict__ L0, const float* __restrict__ L
         for (int c = 0; c < kMaxClasses; ++c) if (c < C) G[c * pitch + j] = 0.f;
       } else {
         const float lse = up_logits(L, st, n, C, w, by, bx, v);
+        float pick = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) if (c < C) G[c * pitch + j] = __expf(v[c] - lse) - (c == (int)lab ? 1.f : 0.f);
+        for (int c = 0; c < kMaxClasses; ++c) if (c < C) {
+          G[c * pitch + j] = __expf(v[c] - lse) - (c == (int)lab ? 1.f : 0.f);
+          if (c == (int)lab) pick = v[c];
+        }
+        if (LOSS) { loss_acc += (double)(lse - pick); cnt_acc += 1.0; }
       }
     }
     __syncthreads();
@@ -223,6 +234,15 @@ dsn_ce_bwd_rows_kernel(const float* __restrict__ L0, const float* __restrict__ L
       for (int j = first[x]; j < first[x + 1]; ++j) a += wa[j] * g[j];
       if (x > 0) for (int j = first[x - 1]; j < first[x]; ++j) a += wb[j] * g[j];
       if (X0 == 0) out[pair] = a; else out[pair] += a;
+    }
+  }
+  if (LOSS) {                                                    // fixed-order partials: one per (head, image, output row)
+    const double tl = block_sum_d(loss_acc, shd);
+    const double tc = block_sum_d(cnt_acc, shd);
+    if (threadIdx.x == 0) {
+      const size_t idx = ((size_t)head * N + n) * H + Y;
+      part_loss[idx] = tl * (double)(head == 0 ? w0 : w1);
+      part_cnt[idx] = head == 0 ? tc : 0.0;
     }
   }
 }
@@ -487,26 +507,67 @@ extern "C" long long skd_dsn_ce_bwd_workspace_floats(int N, int C, int w, int H,
   return (long long)heads * N * H * C * w;
 }
 
+static int dsn_rows_launch(bool with_loss, int N, int C, int h, int w, int H, int W, const float* L0, Strides a, const float* L1, Strides b,
+                           const long long* labels, int ignore_index, float w0, float w1, float* T1, double* part_loss, double* part_cnt,
+                           cudaStream_t st, const char* who) {
+  const int heads = L1 ? 2 : 1;
+  int chunk = W < 1024 ? W : 1024;
+  const size_t smem = ((size_t)C * (chunk | 1) + 2 * (size_t)chunk + (size_t)w + 2) * sizeof(float);
+  if (smem > 200 * 1024) { set_error_msg(who, "source width too large for one block's shared memory"); return 0; }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  if (with_loss)
+    dsn_ce_bwd_rows_kernel<true><<<dim3(H, N, heads), 1024, smem, st>>>(L0, L1, a, b, labels, N, C, h, w, H, W, ignore_index, T1, chunk, part_loss,
+                                                                      part_cnt, w0, w1);
+  else
+    dsn_ce_bwd_rows_kernel<false><<<dim3(H, N, heads), 1024, smem, st>>>(L0, L1, a, b, labels, N, C, h, w, H, W, ignore_index, T1, chunk, nullptr,
+                                                                       nullptr, w0, w1);
+  return 1;
+}
+
 extern "C" int skd_dsn_ce_bwd(int N, int C, int h, int w, int H, int W, const float* L0, long long a_sn, long long a_sc,
                               long long a_sp, const float* L1, long long b_sn, long long b_sc, long long b_sp,
                               const long long* labels, int ignore_index, float w0, float w1, const float* grad_out,
                               const float* count, float* d0, float* d1, float* workspace, cudaStream_t st) {
   if (C > kMaxClasses) { set_error_msg("skd_dsn_ce_bwd", "C > 32 classes unsupported"); return 0; }
   const int heads = L1 ? 2 : 1;
-  int chunk = W < 1024 ? W : 1024;
-  const size_t smem = ((size_t)C * (chunk | 1) + 2 * (size_t)chunk + (size_t)w + 2) * sizeof(float);
-  if (smem > 200 * 1024) { set_error_msg("skd_dsn_ce_bwd", "source width too large for one block's shared memory"); return 0; }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
-  dsn_ce_bwd_rows_kernel<<<dim3(H, N, heads), 1024, smem, st>>>(L0, L1, Strides{a_sn, a_sc, a_sp}, Strides{b_sn, b_sc, b_sp},
-                                                               labels, N, C, h, w, H, W, ignore_index, workspace, chunk);
+  if (!dsn_rows_launch(false, N, C, h, w, H, W, L0, Strides{a_sn, a_sc, a_sp}, L1, Strides{b_sn, b_sc, b_sp}, labels, ignore_index, w0, w1, workspace,
+                       nullptr, nullptr, st, "skd_dsn_ce_bwd")) return 0;
   const long long tot = (long long)heads * N * h * C * w;
   dsn_ce_bwd_cols_kernel<<<red_blocks(tot), 256, 0, st>>>(workspace, d0, L1 ? d1 : nullptr, Strides{a_sn, a_sc, a_sp},
                                                          Strides{b_sn, b_sc, b_sp}, N, C, h, w, H, grad_out, count, w0, w1);
   return finish("skd_dsn_ce_bwd", 2);
+}
+
+// Training forward: loss and valid-pixel count AND the backward's row-phase result (rows_ws: skd_dsn_ce_bwd_workspace_floats) in one
+// pass over the upsampled pixels; partials: 2 * heads * N * H doubles.
+extern "C" long long skd_dsn_ce_train_partials(int N, int H, int heads) { return 2LL * heads * N * H; }
+
+extern "C" int skd_dsn_ce_fwd_train(int N, int C, int h, int w, int H, int W, const float* L0, long long a_sn, long long a_sc,
+                                    long long a_sp, const float* L1, long long b_sn, long long b_sc, long long b_sp,
+                                    const long long* labels, int ignore_index, float w0, float w1, float* loss, float* count,
+                                    double* partials, float* rows_ws, cudaStream_t st) {
+  if (C > kMaxClasses) { set_error_msg("skd_dsn_ce_fwd_train", "C > 32 classes unsupported"); return 0; }
+  const int heads = L1 ? 2 : 1;
+  const int np = heads * N * H;
+  if (!dsn_rows_launch(true, N, C, h, w, H, W, L0, Strides{a_sn, a_sc, a_sp}, L1, Strides{b_sn, b_sc, b_sp}, labels, ignore_index, w0, w1, rows_ws,
+                       partials, partials + np, st, "skd_dsn_ce_fwd_train")) return 0;
+  finalize_sum_kernel<<<1, 256, 0, st>>>(partials, np, 1.0, loss, partials + np, 1, count);
+  return finish("skd_dsn_ce_fwd_train", 2);
+}
+
+// Backward after skd_dsn_ce_fwd_train: only the column phase (d logits = g / count * U_y^T rows_ws)
+extern "C" int skd_dsn_ce_bwd_cols(int N, int C, int h, int w, int H, const float* rows_ws, long long a_sn, long long a_sc, long long a_sp,
+                                   long long b_sn, long long b_sc, long long b_sp, int heads, float w0, float w1, const float* grad_out,
+                                   const float* count, float* d0, float* d1, cudaStream_t st) {
+  const long long tot = (long long)heads * N * h * C * w;
+  dsn_ce_bwd_cols_kernel<<<red_blocks(tot), 256, 0, st>>>(rows_ws, d0, heads == 2 ? d1 : nullptr, Strides{a_sn, a_sc, a_sp},
+                                                         Strides{b_sn, b_sc, b_sp}, N, C, h, w, H, grad_out, count, w0, w1);
+  return finish("skd_dsn_ce_bwd_cols");
 }
 
 extern "C" int skd_pairwise_pool(int N, int C, int H, int W, const float* F, long long sn, long long sc, long long sp,

@@ -17,6 +17,14 @@ __host__ __device__ inline int pool_out_ceil(int in, int k, int s, int p) {
   return o;
 }
 
+// grid (rows, slices of a row): ~4 float4 per thread and slice
+dim3 row_grid(int rows, int per_row) {
+  int ys = (per_row + 1023) / 1024;
+  if (ys < 1) ys = 1;
+  if (ys > 64) ys = 64;
+  return dim3((unsigned)rows, (unsigned)ys);
+}
+
 int ew_blocks(long long total) {
   long long b = (total + 255) / 256;
   if (b > kNumSMs * 16) b = kNumSMs * 16;
@@ -31,13 +39,18 @@ __device__ __forceinline__ void max4(float4& best, int4& bi, const float4 v, int
   if (v.w > best.w || v.w != v.w) { best.w = v.w; bi.w = idx; }
 }
 
+// One block per (output row, slice of the row): the (n, y) decomposition is done once per block and the inner index is 32-bit (the
+// flat 64-bit i -> (n, y, x, c4) chain of divisions cost more issue slots than the memory traffic: ncu put these kernels at 40-60 % of
+// the HBM rate of a plain copy).
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ arg, int N, int H, int W,
                    int C4, int OH, int OW) {
-  const long long total = (long long)N * OH * OW * C4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4); long long r = i / C4;
-    const int ox = (int)(r % OW); r /= OW; const int oy = (int)(r % OH); const int n = (int)(r / OH);
+  const int row = blockIdx.x, n = row / OH, oy = row - n * OH;
+  const int per = OW * C4;
+  const float4* xin = reinterpret_cast<const float4*>(x) + (long long)n * H * W * C4;
+  const long long obase = (long long)row * per;
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per; j += gridDim.y * blockDim.x) {
+    const int ox = j / C4, c4 = j - ox * C4;
     float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); int4 bi = make_int4(0, 0, 0, 0);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -47,11 +60,11 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned 
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = ox * 2 - 1 + kx;
         if (ix < 0 || ix >= W) continue;
-        max4(best, bi, __ldg(reinterpret_cast<const float4*>(x) + (((long long)n * H + iy) * W + ix) * C4 + c4), ky * 3 + kx);
+        max4(best, bi, __ldg(xin + ((long long)iy * W + ix) * C4 + c4), ky * 3 + kx);
       }
     }
-    reinterpret_cast<float4*>(y)[i] = best;
-    reinterpret_cast<uchar4*>(arg)[i] = make_uchar4(bi.x, bi.y, bi.z, bi.w);
+    reinterpret_cast<float4*>(y)[obase + j] = best;
+    reinterpret_cast<uchar4*>(arg)[obase + j] = make_uchar4(bi.x, bi.y, bi.z, bi.w);
   }
 }
 
@@ -59,10 +72,11 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned 
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ arg, float* __restrict__ dx, int N, int H,
                    int W, int C4, int OH, int OW) {
-  const long long total = (long long)N * H * W * C4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4); long long r = i / C4;
-    const int ix = (int)(r % W); r /= W; const int iy = (int)(r % H); const int n = (int)(r / H);
+  const int row = blockIdx.x, n = row / H, iy = row - n * H;
+  const int per = W * C4;
+  const long long ibase = (long long)row * per, nbase = (long long)n * OH * OW * C4;
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per; j += gridDim.y * blockDim.x) {
+    const int ix = j / C4, c4 = j - ix * C4;
     float4 g = make_float4(0, 0, 0, 0);
     for (int oy = iy / 2; oy <= (iy + 1) / 2 && oy < OH; ++oy) {
       const int ky = iy - (oy * 2 - 1);
@@ -70,7 +84,7 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict
       for (int ox = (ix) / 2; ox <= (ix + 1) / 2 && ox < OW; ++ox) {
         const int kx = ix - (ox * 2 - 1);
         if (kx < 0 || kx > 2) continue;
-        const long long o = (((long long)n * OH + oy) * OW + ox) * C4 + c4;
+        const long long o = nbase + ((long long)oy * OW + ox) * C4 + c4;
         const uchar4 a = reinterpret_cast<const uchar4*>(arg)[o];
         const float4 d = __ldg(reinterpret_cast<const float4*>(dy) + o);
         const int k = ky * 3 + kx;
@@ -80,7 +94,7 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict
         if (a.w == k) g.w += d.w;
       }
     }
-    reinterpret_cast<float4*>(dx)[i] = g;
+    reinterpret_cast<float4*>(dx)[ibase + j] = g;
   }
 }
 
@@ -153,31 +167,37 @@ psp_colbins_kernel(const float* __restrict__ rowbins, int C, int H, int W, Pyram
   pooled[((size_t)n * gridDim.x + bin) * C + c] = a / (float)((y1 - y0) * (x1 - x0));
 }
 
-// dx[n][y][x][c] = sum over bins containing (y,x) of dpooled/area
+// dx[n][y][x][c] = sum over bins containing (y,x) of dpooled/area.  Bin extents come from tables in the kernel parameters (the version
+// that re-derived them with integer divisions per element and candidate bin spent ~3 600 instructions per float4: 0.43 ms for 137 MB).
+struct PyrBins { int levels; int size[4]; int first_bin[4]; int lo_y[4][6], hi_y[4][6], lo_x[4][6], hi_x[4][6]; };
+
 __global__ void __launch_bounds__(256)
-psp_pool_bwd_kernel(const float* __restrict__ dpooled, int C4, int H, int W, int N, Pyramid p, int nbins,
+psp_pool_bwd_kernel(const float* __restrict__ dpooled, int C4, int H, int W, int N, PyrBins p, int nbins,
                     float* __restrict__ dx) {
-  const long long total = (long long)N * H * W * C4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4); long long r = i / C4;
-    const int xx = (int)(r % W); r /= W; const int yy = (int)(r % H); const int n = (int)(r / H);
+  const int row = blockIdx.x, n = row / H, yy = row - n * H;
+  const int per = W * C4;
+  const float4* dp = reinterpret_cast<const float4*>(dpooled) + (size_t)n * nbins * C4;
+  const long long obase = (long long)row * per;
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per; j += gridDim.y * blockDim.x) {
+    const int xx = j / C4, c4 = j - xx * C4;
     float4 g = make_float4(0, 0, 0, 0);
-    for (int l = 0; l < p.levels; ++l) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      if (l >= p.levels) break;
       const int s = p.size[l];
-      const int cy = (yy * s) / H, cxb = (xx * s) / W;           // the bin that certainly holds the pixel; neighbours may overlap
-      for (int by = max(cy - 1, 0); by <= min(cy + 1, s - 1); ++by) {
-        const int y0 = bin_lo(by, H, s), y1 = bin_hi(by, H, s);
-        if (yy < y0 || yy >= y1) continue;
-        for (int bx = max(cxb - 1, 0); bx <= min(cxb + 1, s - 1); ++bx) {
-          const int x0 = bin_lo(bx, W, s), x1 = bin_hi(bx, W, s);
-          if (xx < x0 || xx >= x1) continue;
-          const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
-          const float4 d = __ldg(reinterpret_cast<const float4*>(dpooled) + ((size_t)n * nbins + p.first_bin[l] + by * s + bx) * C4 + c4);
+#pragma unroll
+      for (int by = 0; by < 6; ++by) {
+        if (by >= s || yy < p.lo_y[l][by] || yy >= p.hi_y[l][by]) continue;
+#pragma unroll
+        for (int bx = 0; bx < 6; ++bx) {
+          if (bx >= s || xx < p.lo_x[l][bx] || xx >= p.hi_x[l][bx]) continue;
+          const float inv = 1.f / (float)((p.hi_y[l][by] - p.lo_y[l][by]) * (p.hi_x[l][bx] - p.lo_x[l][bx]));
+          const float4 d = __ldg(dp + (size_t)(p.first_bin[l] + by * s + bx) * C4 + c4);
           g.x += d.x * inv; g.y += d.y * inv; g.z += d.z * inv; g.w += d.w * inv;
         }
       }
     }
-    reinterpret_cast<float4*>(dx)[i] = g;
+    reinterpret_cast<float4*>(dx)[obase + j] = g;
   }
 }
 
@@ -194,20 +214,28 @@ __device__ __forceinline__ Lin lin(int dst, int in, int out) {
 __global__ void __launch_bounds__(256)
 psp_up_fwd_kernel(const float* __restrict__ src, int C4, int s, int nb_total, int first_bin, float* __restrict__ out,
                   int out_pitch4, int coff4, int N, int H, int W) {
-  const long long total = (long long)N * H * W * C4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4); long long r = i / C4;
-    const int xx = (int)(r % W); r /= W; const int yy = (int)(r % H); const int n = (int)(r / H);
-    const Lin by = lin(yy, s, H), bx = lin(xx, s, W);
-    const float4* b = reinterpret_cast<const float4*>(src) + ((size_t)n * nb_total + first_bin) * C4 + c4;
-    const float4 v00 = __ldg(b + (size_t)(by.i0 * s + bx.i0) * C4), v01 = __ldg(b + (size_t)(by.i0 * s + bx.i1) * C4);
-    const float4 v10 = __ldg(b + (size_t)(by.i1 * s + bx.i0) * C4), v11 = __ldg(b + (size_t)(by.i1 * s + bx.i1) * C4);
+  const int row = blockIdx.x, n = row / H, yy = row - n * H;
+  const int per = W * C4;
+  const Lin by = lin(yy, s, H);
+  const float4* b = reinterpret_cast<const float4*>(src) + ((size_t)n * nb_total + first_bin) * C4;
+  const float4* r0 = b + (size_t)(by.i0 * s) * C4;
+  const float4* r1 = b + (size_t)(by.i1 * s) * C4;
+  float4* orow = reinterpret_cast<float4*>(out) + (size_t)row * W * out_pitch4 + coff4;
+  const float scale = W > 1 ? (float)(s - 1) / (float)(W - 1) : 0.f;
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < per; j += gridDim.y * blockDim.x) {
+    const int xx = j / C4, c4 = j - xx * C4;
+    const float sx = scale * (float)xx;                                  // lin(xx, s, W) with the scale hoisted
+    int i0 = (int)sx; if (i0 > s - 1) i0 = s - 1;
+    const int i1 = i0 + (i0 < s - 1 ? 1 : 0);
+    const float l1 = sx - (float)i0, l0 = 1.f - l1;
+    const float4 v00 = __ldg(r0 + (size_t)i0 * C4 + c4), v01 = __ldg(r0 + (size_t)i1 * C4 + c4);
+    const float4 v10 = __ldg(r1 + (size_t)i0 * C4 + c4), v11 = __ldg(r1 + (size_t)i1 * C4 + c4);
     float4 o;
-    o.x = by.l0 * (bx.l0 * v00.x + bx.l1 * v01.x) + by.l1 * (bx.l0 * v10.x + bx.l1 * v11.x);
-    o.y = by.l0 * (bx.l0 * v00.y + bx.l1 * v01.y) + by.l1 * (bx.l0 * v10.y + bx.l1 * v11.y);
-    o.z = by.l0 * (bx.l0 * v00.z + bx.l1 * v01.z) + by.l1 * (bx.l0 * v10.z + bx.l1 * v11.z);
-    o.w = by.l0 * (bx.l0 * v00.w + bx.l1 * v01.w) + by.l1 * (bx.l0 * v10.w + bx.l1 * v11.w);
-    reinterpret_cast<float4*>(out)[(((size_t)n * H + yy) * W + xx) * out_pitch4 + coff4 + c4] = o;
+    o.x = by.l0 * (l0 * v00.x + l1 * v01.x) + by.l1 * (l0 * v10.x + l1 * v11.x);
+    o.y = by.l0 * (l0 * v00.y + l1 * v01.y) + by.l1 * (l0 * v10.y + l1 * v11.y);
+    o.z = by.l0 * (l0 * v00.z + l1 * v01.z) + by.l1 * (l0 * v10.z + l1 * v11.z);
+    o.w = by.l0 * (l0 * v00.w + l1 * v01.w) + by.l1 * (l0 * v10.w + l1 * v11.w);
+    orow[(size_t)xx * out_pitch4 + c4] = o;
   }
 }
 
@@ -306,7 +334,7 @@ extern "C" int skd_maxpool3x3s2_fwd(int N, int H, int W, int C, const float* x, 
                                     cudaStream_t st) {
   if (C % 4) { set_error_msg("skd_maxpool3x3s2_fwd", "C % 4 != 0"); return 0; }
   const int OH = pool_out_ceil(H, 3, 2, 1), OW = pool_out_ceil(W, 3, 2, 1);
-  maxpool_fwd_kernel<<<ew_blocks((long long)N * OH * OW * (C / 4)), 256, 0, st>>>(x, y, argmax, N, H, W, C / 4, OH, OW);
+  maxpool_fwd_kernel<<<row_grid(N * OH, OW * (C / 4)), 256, 0, st>>>(x, y, argmax, N, H, W, C / 4, OH, OW);
   return finish("skd_maxpool3x3s2_fwd");
 }
 
@@ -314,7 +342,7 @@ extern "C" int skd_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy,
                                     cudaStream_t st) {
   if (C % 4) { set_error_msg("skd_maxpool3x3s2_bwd", "C % 4 != 0"); return 0; }
   const int OH = pool_out_ceil(H, 3, 2, 1), OW = pool_out_ceil(W, 3, 2, 1);
-  maxpool_bwd_kernel<<<ew_blocks((long long)N * H * W * (C / 4)), 256, 0, st>>>(dy, argmax, dx, N, H, W, C / 4, OH, OW);
+  maxpool_bwd_kernel<<<row_grid(N * H, W * (C / 4)), 256, 0, st>>>(dy, argmax, dx, N, H, W, C / 4, OH, OW);
   return finish("skd_maxpool3x3s2_bwd");
 }
 
@@ -359,15 +387,25 @@ extern "C" int skd_psp_pool_bwd(int N, int H, int W, int C, const float* dpooled
                                 cudaStream_t st) {
   if (C % 4 || levels < 1 || levels > 4) { set_error_msg("skd_psp_pool_bwd", "C % 4 != 0 or bad levels"); return 0; }
   const Pyramid p = make_pyramid(levels, sizes);
-  psp_pool_bwd_kernel<<<ew_blocks((long long)N * H * W * (C / 4)), 256, 0, st>>>(dpooled, C / 4, H, W, N, p, p.first_bin[levels], dx);
+  PyrBins pb; pb.levels = levels;
+  for (int l = 0; l < 4; ++l) {
+    pb.size[l] = l < levels ? sizes[l] : 1; pb.first_bin[l] = l < levels ? p.first_bin[l] : 0;
+    if (pb.size[l] > 6) { set_error_msg("skd_psp_pool_bwd", "pyramid level size must be <= 6"); return 0; }
+    for (int b = 0; b < 6; ++b) {
+      const bool ok = l < levels && b < sizes[l];
+      pb.lo_y[l][b] = ok ? (b * H) / sizes[l] : 0; pb.hi_y[l][b] = ok ? ((b + 1) * H + sizes[l] - 1) / sizes[l] : 0;
+      pb.lo_x[l][b] = ok ? (b * W) / sizes[l] : 0; pb.hi_x[l][b] = ok ? ((b + 1) * W + sizes[l] - 1) / sizes[l] : 0;
+    }
+  }
+  psp_pool_bwd_kernel<<<row_grid(N * H, W * (C / 4)), 256, 0, st>>>(dpooled, C / 4, H, W, N, pb, p.first_bin[levels], dx);
   return finish("skd_psp_pool_bwd");
 }
 
 extern "C" int skd_psp_upsample_fwd(int N, int H, int W, int C, int s, const float* src, int nbins_total, int first_bin,
                                     float* out, int out_pitch, int chan_off, cudaStream_t st) {
   if (C % 4 || out_pitch % 4 || chan_off % 4) { set_error_msg("skd_psp_upsample_fwd", "channel counts must be multiples of 4"); return 0; }
-  psp_up_fwd_kernel<<<ew_blocks((long long)N * H * W * (C / 4)), 256, 0, st>>>(src, C / 4, s, nbins_total, first_bin, out,
-                                                                              out_pitch / 4, chan_off / 4, N, H, W);
+  psp_up_fwd_kernel<<<row_grid(N * H, W * (C / 4)), 256, 0, st>>>(src, C / 4, s, nbins_total, first_bin, out,
+                                                                 out_pitch / 4, chan_off / 4, N, H, W);
   return finish("skd_psp_upsample_fwd");
 }
 

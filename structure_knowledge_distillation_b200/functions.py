@@ -57,17 +57,29 @@ class DsnCrossEntropy(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, l0, l1, labels, ignore_index, w0, w1):
-        out = ops.dsn_ce_fwd(l0, l1, labels, ignore_index, w0, w1)
-        ctx.save_for_backward(l0, l1, labels, out)
+        # with a backward to come, the forward pass over the upsampled pixels already leaves the backward's row-phase result behind
+        # (one softmax per pixel and step instead of two); inference keeps the plain forward
+        ctx.fused = l0.requires_grad or (l1 is not None and l1.requires_grad)
+        if ctx.fused:
+            out, rows = ops.dsn_ce_fwd_train(l0, l1, labels, ignore_index, w0, w1)
+            ctx.save_for_backward(l0, l1, rows, out)
+            ctx.H = labels.shape[1]
+        else:
+            out = ops.dsn_ce_fwd(l0, l1, labels, ignore_index, w0, w1)
+            ctx.save_for_backward(l0, l1, labels, out)
         ctx.cfg = (ignore_index, w0, w1)
         return out[0].clone()
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        l0, l1, labels, out = ctx.saved_tensors
         ig, w0, w1 = ctx.cfg
-        d0, d1 = ops.dsn_ce_bwd(l0, l1, labels, ig, w0, w1, g.contiguous(), out[1])
+        if ctx.fused:
+            l0, l1, rows, out = ctx.saved_tensors
+            d0, d1 = ops.dsn_ce_bwd_cols(l0, l1, rows, ctx.H, w0, w1, g.contiguous(), out[1])
+        else:
+            l0, l1, labels, out = ctx.saved_tensors
+            d0, d1 = ops.dsn_ce_bwd(l0, l1, labels, ig, w0, w1, g.contiguous(), out[1])
         return d0, d1, None, None, None, None
 
 

@@ -135,9 +135,22 @@ class NetModel():
     def set_input(self, data):
         images, labels = data[0], data[1]
         if self._graphs is not None and self._graphs.get("captured"):
-            # replayed CUDA graphs read fixed device buffers: copy the new batch into them
-            self.images.copy_(images, non_blocking=True)
-            self.labels.copy_(labels, non_blocking=True)
+            # replayed CUDA graphs read fixed device buffers.  The host -> device copy of the next batch goes to a STAGING pair on a
+            # copy stream, so it runs while the previous step's graph is still executing (set_input returns immediately when the source
+            # is pinned); optimize_parameters() moves staging -> static buffers (a 0.1 GB device copy) right before the replay.
+            g = self._graphs
+            if "stage_images" not in g:
+                g["stage_images"], g["stage_labels"] = torch.empty_like(self.images), torch.empty_like(self.labels)
+                g["copy_stream"] = torch.cuda.Stream()
+                g["staged"], g["consumed"] = torch.cuda.Event(), None
+            cs = g["copy_stream"]
+            if g["consumed"] is not None:
+                cs.wait_event(g["consumed"])                          # the previous batch has left the staging buffers
+            with torch.cuda.stream(cs):
+                g["stage_images"].copy_(images, non_blocking=True)
+                g["stage_labels"].copy_(labels, non_blocking=True)
+                g["staged"].record(cs)
+            g["pending"] = True
             return
         self.images = images.to(self.device, non_blocking=True)
         self.labels = labels.long().to(self.device, non_blocking=True)
@@ -315,6 +328,13 @@ class NetModel():
             self._updates()
             g["captured"] = True
             return
+        if g.get("pending"):                                        # staged batch -> the graph's static input buffers
+            cur = torch.cuda.current_stream()
+            cur.wait_event(g["staged"])
+            self.images.copy_(g["stage_images"], non_blocking=True)
+            self.labels.copy_(g["stage_labels"], non_blocking=True)
+            g["consumed"] = torch.cuda.Event(); g["consumed"].record(cur)
+            g["pending"] = False
         g["student"].replay()
         self._updates()
 

@@ -425,6 +425,34 @@ def dsn_ce_fwd(l0, l1, labels, ignore_index, w0, w1):
     return out
 
 
+def dsn_ce_fwd_train(l0, l1, labels, ignore_index, w0, w1):
+    """Training forward: (loss, count) tensor AND the backward's row-phase workspace, in one pass over the upsampled pixels."""
+    _f32(l0, l1)
+    n, c, h, w = l0.shape
+    H, W = labels.shape[1:]
+    if labels.dtype != torch.int64 or not labels.is_contiguous():
+        raise ValueError("labels must be contiguous int64")
+    L = lib()
+    heads = 2 if l1 is not None else 1
+    out = torch.empty(2, device=l0.device, dtype=torch.float32)       # loss, valid count
+    parts = torch.empty(L.skd_dsn_ce_train_partials(n, H, heads), device=l0.device, dtype=torch.float64)
+    rows = torch.empty(L.skd_dsn_ce_bwd_workspace_floats(n, c, w, H, heads), device=l0.device, dtype=torch.float32)
+    s1 = pixel_strides(l1) if l1 is not None else (0, 0, 0)
+    L.skd_dsn_ce_fwd_train(n, c, h, w, H, W, _p(l0), *pixel_strides(l0), _p(l1), *s1, _p(labels), ignore_index, w0, w1,
+                           _p(out[0]), _p(out[1]), _p(parts), _p(rows), _st())
+    return out, rows
+
+
+def dsn_ce_bwd_cols(l0, l1, rows, H, w0, w1, grad_out, count):
+    n, c, h, w = l0.shape
+    d0 = torch.empty_strided(l0.shape, l0.stride(), device=l0.device, dtype=torch.float32)
+    d1 = torch.empty_strided(l1.shape, l1.stride(), device=l1.device, dtype=torch.float32) if l1 is not None else None
+    s1 = pixel_strides(l1) if l1 is not None else (0, 0, 0)
+    lib().skd_dsn_ce_bwd_cols(n, c, h, w, H, _p(rows), *pixel_strides(l0), *s1, 2 if l1 is not None else 1, w0, w1, _p(grad_out), _p(count),
+                              _p(d0), _p(d1), _st())
+    return d0, d1
+
+
 def dsn_ce_bwd(l0, l1, labels, ignore_index, w0, w1, grad_out, count):
     n, c, h, w = l0.shape
     H, W = labels.shape[1:]

@@ -98,15 +98,17 @@ class FlatSGD:
                 which[i] = bi
         self._side = torch.cuda.Stream()
         self._active = False
+        self._arrival_log = None                                     # debugging aid: list -> (param index, via) per arrival
         for i, p in enumerate(self.params):
-            p.register_post_accumulate_grad_hook(lambda _p, bi=which[i]: self._arrived(bi))
-            p._skd_arrived = (lambda bi=which[i]: self._arrived(bi))     # called by backward kernels that wrote p._skd_grad directly
+            p.register_post_accumulate_grad_hook(lambda _p, bi=which[i], i=i: self._arrived(bi, i, "hook"))
+            p._skd_arrived = (lambda bi=which[i], i=i: self._arrived(bi, i, "direct"))   # called by backward kernels that wrote p._skd_grad directly
 
     def begin_overlapped_reduce(self, world):
         self._world = world
         self.grad_scale = 1.0 / world if world > 1 else 1.0
         for b in self._buckets:
             b["left"], b["sent"] = b["hi"] - b["lo"], False
+        self._got = bytearray(len(self.params))
         self._active = world > 1
 
     def _send(self, b):
@@ -118,9 +120,17 @@ class FlatSGD:
         with torch.cuda.stream(self._side):
             dist.all_reduce(self.flat_g[b["start"]:b["end"]], op=dist.ReduceOp.SUM)
 
-    def _arrived(self, bi):
+    def _arrived(self, bi, i=None, via=None):
+        if self._arrival_log is not None:
+            self._arrival_log.append((i, via))
         if not self._active:
             return
+        # a parameter counts ONCE per pass: a gradient the kernels wrote directly reports itself (functions._grad_written) and the
+        # autograd engine may still run the parameter's post-accumulate hook for the `None` the backward returned (torch 2.11 does)
+        if i is not None:
+            if self._got[i]:
+                return
+            self._got[i] = 1
         b = self._buckets[bi]
         b["left"] -= 1
         if b["left"] == 0 and not b["sent"]:

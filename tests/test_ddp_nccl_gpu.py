@@ -47,7 +47,8 @@ def _worker(rank, world, port, out):
         ref_sum = sum(parts)
         err = float((summed - ref_sum).norm() / ref_sum.norm())
         assert err < 1e-6, err
-        # second pass over the same weights / inputs with the bucketed all-reduce issued from inside backward: same sums, bit for bit
+        # second pass over the same weights / inputs with the bucketed all-reduce issued from inside backward (gradients written directly into
+        # the flat buffer report themselves; the weight-gradient stream is a producer the NCCL stream waits for): same sums
         m.G_solver._buckets = buckets
         with torch.no_grad():
             for k, v in m.D_model.state_dict().items():
@@ -55,7 +56,9 @@ def _worker(rank, world, port, out):
         m._student_phase()
         assert m._g_reduced
         torch.cuda.synchronize()
-        assert torch.equal(m.G_solver.flat_g, summed), float((m.G_solver.flat_g - summed).abs().max())
+        # same sums (three conv-bias gradients come from an atomicAdd column sum: last-bit differences between two passes are expected)
+        err_o = float((m.G_solver.flat_g - summed).norm() / summed.norm())
+        assert err_o < 1e-6, (err_o, float((m.G_solver.flat_g - summed).abs().max()))
         lr, mom, wd = m.G_solver.param_groups[0]["lr"], 0.9, m.args.weight_decay
         m.G_solver.step()
         expect = p0 - lr * (ref_sum / world + wd * p0)                               # first step: momentum buffer is zero
