@@ -91,7 +91,13 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
     ptx::fence_barrier_init();
   }
-  constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  // TMEM: 2 accumulator stages x kSub sub-accumulators x BLOCK_N columns = all 512.  Split precision spreads the filter taps of a tile
+  // over the kSub sub-accumulators and adds them in the epilogue with round-to-nearest fp32 adds: the tensor core TRUNCATES when it adds
+  // into its accumulator (~2^-24 relative, biased, per MMA), and with 216 MMAs per tile that truncation -- not the operand split -- was
+  // what was left of the error of the "fp32-grade" layers (~1e-5), which train-mode BN then amplifies ~50x into the pair-wise loss.
+  constexpr int kSub = 256 / BLOCK_N;                  // 4 (BLOCK_N 64) or 2 (128)
+  constexpr int kTmemCols = 512;
+  const int nsub = split3 ? kSub : 1;
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_base_slot);
   ptx::tc_fence_before();
   if constexpr (CL > 1) ptx::cluster_sync(); else __syncthreads();     // peers' barriers exist before anything is multicast to them
@@ -158,7 +164,8 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       __syncwarp();
       ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * kSub * BLOCK_N);
+      uint32_t used = 0;                                                            // sub-accumulators that already hold a partial sum
       for (int kc = 0; kc < a.k_chunks; ++kc) {
         if (lane == 0) {
           ptx::mbar_wait(&a_full[slot], sphase);
@@ -175,16 +182,19 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
             const int kh = tap / 3, kw = tap - kh * 3;
             const uint32_t sa = sa0 + (uint32_t)((kh * kHW + kw) * 128);          // shifted view of the halo tile
             const uint32_t sb = ptx::smem_u32(sB + (WRES ? kc * 9 + tap : stage) * stage_stride);
+            const int sub = tap % nsub;
+            const uint32_t tmem_d = tmem_acc + (uint32_t)(sub * BLOCK_N);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, kHW * 128);   // 8-pixel groups one halo row apart
               const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 32, 16, 1024);
-              ptx::mma_tf32(tmem_d, da, db, idesc, (kc | tap | kk) != 0 ? 1u : 0u);
+              ptx::mma_tf32(tmem_d, da, db, idesc, ((used >> sub) & 1u) | (kk != 0 ? 1u : 0u));
               if (split3) {
                 ptx::mma_tf32(tmem_d, ptx::make_smem_desc_sw128(sa + kSlotBytes + kk * 32, 16, kHW * 128), db, idesc, 1u);
                 ptx::mma_tf32(tmem_d, da, ptx::make_smem_desc_sw128(sb + kBBytes + kk * 32, 16, 1024), idesc, 1u);
               }
             }
+            used |= 1u << sub;
             if constexpr (!WRES) ptx::mma_commit(&b_empty[stage]);
             if constexpr (CL > 1) ptx::mma_commit_mcast(&b_empty_all[stage], (uint16_t)1);   // ... and tell the leader
             if (tap == 8) {
@@ -222,7 +232,7 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kSub * BLOCK_N);
 #pragma unroll 1
       for (int ch = group; ch < BLOCK_N / 32; ch += 2) {
         const int c0 = ch * 32;
@@ -230,6 +240,13 @@ conv3x3_halo_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + ch * 32, r);
         ptx::tmem_ld_wait();
+        for (int sb2 = 1; sb2 < nsub; ++sb2) {                                     // split precision: add the other sub-accumulators (RN fp32)
+          uint32_t r2[32];
+          ptx::tmem_ld_32x32(taddr + sb2 * BLOCK_N + ch * 32, r2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         float v[32];
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);

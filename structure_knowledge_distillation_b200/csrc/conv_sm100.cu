@@ -77,7 +77,11 @@ struct Cfg {
   static constexpr int kFixedBytes = 2 * kOutStageBytes + 768 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4;
   static constexpr int kFit = (232448 - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;                           // 4 / 6 / 8 / 8 (PAIR 1), 6 / 8 (PAIR 2)
-  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;       // power of two: 64..512
+  // split precision: the K steps of a tile go round-robin to kSub sub-accumulators that the epilogue adds with round-to-nearest fp32
+  // adds (the tensor core truncates on every accumulate: with hundreds of MMAs per tile that, not the operand split, limited the
+  // "fp32-grade" layers to ~1e-5).  2 stages x kSub x BLOCK_N columns.
+  static constexpr int kSub = BLOCK_N >= 256 ? 1 : (BLOCK_N == 128 ? 2 : 4);
+  static constexpr int kTmemCols = (2 * kSub * BLOCK_N < 32) ? 32 : 2 * kSub * BLOCK_N;       // power of two: 256..512
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
@@ -215,7 +219,9 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       __syncwarp();
       ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * C::kSub * BLOCK_N);
+      const int nsub = split3 ? C::kSub : 1;
+      uint32_t used = 0;
       const int tu = a.reverse ? total_tiles - 1 - tile : tile;
       const int sp = tu % a.splits;
       const int nk = min(k_iters, (sp + 1) * a.k_per_split) - sp * a.k_per_split;      // K steps of this unit (all of them without split-K)
@@ -225,6 +231,8 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * stage_stride);
           const uint32_t sb = sa + kABytes;
+          const int sub = k % nsub;
+          const uint32_t tmem_d = tmem_acc + (uint32_t)(sub * BLOCK_N);
           auto mma = [&](uint64_t da, uint64_t db, uint32_t accumulate) {
             if constexpr (PAIR == 2) ptx::mma_tf32_2cta(tmem_d, da, db, idesc, accumulate);
             else ptx::mma_tf32(tmem_d, da, db, idesc, accumulate);
@@ -233,12 +241,13 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
             const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * kUmmaK * 4, 16, 1024);
             const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * kUmmaK * 4, 16, 1024);
-            mma(da, db, (k | kk) != 0 ? 1u : 0u);
+            mma(da, db, ((used >> sub) & 1u) | (kk != 0 ? 1u : 0u));
             if (split3) {                                       // + x_lo * w_hi + x_hi * w_lo (the lo tiles sit kStageBytes further)
               mma(ptx::make_smem_desc_sw128(sa + C::kStageBytes + kk * kUmmaK * 4, 16, 1024), db, 1u);
               mma(da, ptx::make_smem_desc_sw128(sb + C::kStageBytes + kk * kUmmaK * 4, 16, 1024), 1u);
             }
           }
+          used |= 1u << sub;
           if constexpr (PAIR == 2) {                          // multicast: the stage / accumulator barriers of both CTAs
             ptx::mma_commit_2cta(&empty_bar[stage]);
             if (k == nk - 1) ptx::mma_commit_2cta(&tmem_full[acc]);
@@ -318,7 +327,9 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * C::kSub * BLOCK_N);
+      const int nk_e = min(k_iters, (sp + 1) * a.k_per_split) - sp * a.k_per_split;     // K steps of this unit: sub-accumulators in use
+      const int nsub_e = split3 ? min(C::kSub, nk_e) : 1;
 #pragma unroll 1
       for (int ch = group; ch < BLOCK_N / 32; ch += 2) {
         const int c0 = nt * BLOCK_N + ch * 32;
@@ -341,6 +352,13 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + ch * 32, r);
         ptx::tmem_ld_wait();
+        for (int sb2 = 1; sb2 < nsub_e; ++sb2) {                                  // split precision: the other sub-accumulators (RN fp32 adds)
+          uint32_t r2[32];
+          ptx::tmem_ld_32x32(taddr + sb2 * BLOCK_N + ch * 32, r2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         float v[32];
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale + ch * 32);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift + ch * 32);

@@ -4,6 +4,7 @@ Conventions kept from the reference (libs/functions.py:70-162): ctx.save_for_bac
 arguments get None gradients, backward is once-differentiable (no double backward through hand-written kernels).
 """
 import torch
+import torch.distributed as dist
 from torch.autograd.function import once_differentiable
 
 from . import ops
@@ -149,6 +150,15 @@ def _direct_grad(param, shape_ohwi=None):
     return g
 
 
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _sync_mean(t):
+    dist.all_reduce(t)
+    t /= _world()
+
+
 class WgradOverlap:
     """Weight-gradient kernels on a side stream.  In the backward pass only the data-gradient chain (dgrad -> ABN backward -> dgrad
     ...) is sequential; a layer's weight gradient needs (x, dy) and feeds nothing but the optimizer.  Issued on a second stream the
@@ -259,8 +269,23 @@ class ABN(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, activation, slope, residual,
-                chan_mul):
-        if training:
+                chan_mul, sync=False):
+        ctx.sync = bool(sync) and training and _world() > 1
+        if ctx.sync:
+            # InPlaceABNSync across processes (libs/functions.py:177-209): per-rank mean / biased variance, combined as
+            # mean = E[mean_r], var = E[var_r + (mean - mean_r)^2] (equal per-rank counts, like the reference), running statistics
+            # with the GLOBAL sample count; one small all-reduce per layer and direction
+            loc = ops.abn_stats(x, weight, bias, eps, momentum, None, None)
+            m = torch.stack([loc[0], loc[1] + loc[0] * loc[0]])
+            dist.all_reduce(m)
+            m /= _world()
+            mean, var = m[0], (m[1] - m[0] * m[0]).clamp_min_(0)
+            n = float(x.numel() // x.shape[1]) * _world()
+            running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+            running_var.mul_(1 - momentum).add_(var, alpha=momentum * (n / (n - 1) if n > 1 else 1.0))
+            sc, sh = ops.abn_fold(mean, var, weight, bias, eps)
+            st = torch.stack([mean, var, sc, sh])
+        elif training:
             st = ops.abn_stats(x, weight, bias, eps, momentum, running_mean, running_var)
         else:
             sc, sh = ops.abn_fold(running_mean, running_var, weight, bias, eps)
@@ -287,11 +312,11 @@ class ABN(torch.autograd.Function):
         if gw is None or gb is None:
             gw = gb = None
         dx, dres, dw, db = ops.abn_backward(x, out, ops.to_nhwc(dout), st, weight, eps, activation, slope, chan_mul, has_res,
-                                            training=training, dweight_out=gw, dbias_out=gb)
+                                            training=training, dweight_out=gw, dbias_out=gb, sync_fn=_sync_mean if ctx.sync else None)
         if gw is not None:                                   # the reduce kernel wrote dweight / dbias into the flat gradient buffer
             _grad_written(wparam); _grad_written(bparam)
             dw = db = None
-        return dx, dw, db, None, None, None, None, None, None, None, dres, None
+        return dx, dw, db, None, None, None, None, None, None, None, dres, None, None
 
 
 class MaxPool3x3s2(torch.autograd.Function):

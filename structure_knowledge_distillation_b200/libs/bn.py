@@ -44,7 +44,7 @@ class InPlaceABN(nn.Module):
         elif residual is not None:
             raise ValueError("a fused residual add is only defined together with fuse_relu")
         return Fn.ABN.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.training, self.momentum,
-                            self.eps, act, self.slope, residual, chan_mul)
+                            self.eps, act, self.slope, residual, chan_mul, getattr(self, "sync_stats", False))
 
     def __repr__(self):
         rep = '{name}({num_features}, eps={eps}, momentum={momentum}, affine={affine}, activation={activation}'
@@ -53,7 +53,11 @@ class InPlaceABN(nn.Module):
 
 
 class InPlaceABNSync(InPlaceABN):
-    """Same constructor as libs/bn.py:108-147 (`devices` accepted and ignored: one process per GPU)."""
+    """Same constructor as libs/bn.py:108-147 (`devices` accepted and ignored: one process per GPU).  `sync_stats = True` (per module,
+    or NetModel's `args.sync_bn`) synchronises the batch statistics across the ranks of the default process group the way the
+    reference's multi-GPU mode does across its worker threads (libs/functions.py:177-209,255-283); the default keeps them per rank,
+    which is what the reference's own launch script runs (one GPU)."""
+    sync_stats = False
 
     def __init__(self, num_features, devices=None, eps=1e-5, momentum=0.1, affine=True, activation="leaky_relu", slope=0.01):
         super().__init__(num_features, eps, momentum, affine, activation, slope)

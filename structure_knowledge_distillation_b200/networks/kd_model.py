@@ -70,6 +70,11 @@ class NetModel():
         student = Res_pspnet(BasicBlock, [2, 2, 2, 2], num_classes=args.classes_num)
         load_S_model(args, student, False)                         # ImageNet init or S_resume (utils/utils.py:93-127)
         self.student = student.float().to(device).train()
+        if _arg(args, "sync_bn", False):                          # cross-rank batch statistics (the reference's InPlaceABNSync semantics)
+            from ..libs import InPlaceABNSync
+            for mod in self.student.modules():
+                if isinstance(mod, InPlaceABNSync):
+                    mod.sync_stats = True
         self.parallel_student = self.student
 
         teacher = Res_pspnet(Bottleneck, [3, 4, 23, 3], num_classes=args.classes_num)

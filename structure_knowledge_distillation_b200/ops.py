@@ -129,7 +129,7 @@ def abn_apply(x, scale, shift, act, slope, residual=None, chan_mul=None, out=Non
 
 
 def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dres, round_tf32=False, training=True,
-                 dweight_out=None, dbias_out=None):
+                 dweight_out=None, dbias_out=None, sync_fn=None):
     """-> dx, dres (or None), dweight, dbias.  dweight_out / dbias_out: write the affine gradients there (flat gradient views)."""
     n, c, h, w, pitch = nhwc_meta(x)
     if (out is not None and nhwc_meta(out)[4] != c) or nhwc_meta(dout)[4] != c or pitch != c:
@@ -146,6 +146,8 @@ def abn_backward(x, out, dout, stats, weight, eps, act, slope, chan_mul, want_dr
         L.skd_abn_bwd_reduce_nhwc(P, c, h * w, _p(x), _p(out), _p(dout), _p(stats[0]), _p(stats[1]), _p(weight), eps, ACT[act],
                                   slope, _p(chan_mul), _p(red[0]), _p(red[1]), _p(dwt), _p(dbt), _p(ws), splits, _p(stats[2]), _p(stats[3]),
                                   _st())
+        if sync_fn is not None:                      # synchronised statistics: edz / eydz are means over ALL ranks (functions.py:271-272)
+            sync_fn(red[0:2])
     else:                                            # libs/functions.py:144-147: no batch-statistics terms, zero affine gradients
         red = torch.zeros(4, c, device=dev)
         dwt, dbt = red[2], red[3]

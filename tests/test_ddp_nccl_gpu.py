@@ -88,3 +88,57 @@ def test_two_rank_nccl_gradient_average_through_flat_sgd():
     res = q.get(timeout=10)
     print("\nPARITY nccl_dp_world2", res)
     assert res[0] == "ok", res
+
+
+def _sync_bn_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        from structure_knowledge_distillation_b200 import ops
+        from structure_knowledge_distillation_b200.libs import InPlaceABNSync
+        g = torch.Generator().manual_seed(11)
+        N, C, H, W = 4, 96, 9, 13
+        x = torch.randn(N, C, H, W, generator=g) * 1.7 + 0.4
+        dout = torch.randn(N, C, H, W, generator=g)
+        w0, b0 = torch.randn(C, generator=g), torch.randn(C, generator=g) * 0.2
+
+        def run(xs, ds, sync):
+            bn = InPlaceABNSync(C, activation="leaky_relu", slope=0.01).cuda().train()
+            bn.sync_stats = sync
+            with torch.no_grad():
+                bn.weight.copy_(w0); bn.bias.copy_(b0)
+            xi = ops.to_nhwc(xs.cuda()).requires_grad_(True)
+            y = bn(xi)
+            y.backward(ops.to_nhwc(ds.cuda()))
+            return y.detach(), xi.grad, bn.weight.grad, bn.bias.grad, bn.running_mean.clone(), bn.running_var.clone()
+        half = slice(rank * N // world, (rank + 1) * N // world)
+        y, dx, dw, db, rm, rv = run(x[half], dout[half], True)                 # this rank's shard, synchronised statistics
+        dist.all_reduce(dw); dist.all_reduce(db)                                # parameter gradients: summed over ranks (as the optimizer's exchange does)
+        yf, dxf, dwf, dbf, rmf, rvf = run(x, dout, False)                       # the whole batch on one GPU
+        rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+        errs = dict(y=rel(y, yf[half]), dx=rel(dx, dxf[half]), dw=rel(dw, dwf), db=rel(db, dbf), rm=rel(rm, rmf), rv=rel(rv, rvf))
+        assert max(errs.values()) < 2e-5, errs
+        if rank == 0:
+            out.put(("ok", errs))
+    except Exception as e:                                              # noqa: BLE001
+        out.put(("fail", rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sync_bn_two_ranks_equals_full_batch():
+    """InPlaceABNSync with sync_stats over 2 NCCL ranks, each holding half of a batch (libs/functions.py:177-209,255-283 semantics:
+    combined mean / variance, running statistics with the global count, edz / eydz averaged over ranks) == the whole batch on one GPU:
+    outputs, input gradients, summed parameter gradients, running statistics."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    mp.spawn(_sync_bn_worker, args=(2, 29571, q), nprocs=2, join=True)
+    res = q.get(timeout=30)
+    assert res[0] == "ok", res
+    print("\nPARITY sync_bn_world2", res[1])
