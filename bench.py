@@ -281,7 +281,7 @@ def run_ours(args, rank, local_rank, world):
     def step_resident(i):
         model.adjust_learning_rate(margs.lr_g, model.G_solver, i)
         model.adjust_learning_rate(margs.lr_d, model.D_solver, i)
-        model.images, model.labels = dev_i, dev_l
+        model.set_input((dev_i, dev_l, None, None))                # the batch is already in HBM: set_input() only moves it device -> device
         model.optimize_parameters()
 
     sink = []

@@ -145,7 +145,7 @@ class NetModel():
             # is pinned); optimize_parameters() moves staging -> static buffers (a 0.1 GB device copy) right before the replay.
             g = self._graphs
             if "stage_images" not in g:
-                g["stage_images"], g["stage_labels"] = torch.empty_like(self.images), torch.empty_like(self.labels)
+                g["stage_images"], g["stage_labels"] = torch.empty_like(g["static_images"]), torch.empty_like(g["static_labels"])
                 g["copy_stream"] = torch.cuda.Stream()
                 g["staged"], g["consumed"] = torch.cuda.Event(), None
             cs = g["copy_stream"]
@@ -326,6 +326,7 @@ class NetModel():
                 return
             # static input buffers + capture
             self.images = self.images.clone(); self.labels = self.labels.clone()
+            g["static_images"], g["static_labels"] = self.images, self.labels     # what the captured kernels read
             torch.cuda.synchronize()
             g["student"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g["student"]):
@@ -336,8 +337,9 @@ class NetModel():
         if g.get("pending"):                                        # staged batch -> the graph's static input buffers
             cur = torch.cuda.current_stream()
             cur.wait_event(g["staged"])
-            self.images.copy_(g["stage_images"], non_blocking=True)
-            self.labels.copy_(g["stage_labels"], non_blocking=True)
+            g["static_images"].copy_(g["stage_images"], non_blocking=True)
+            g["static_labels"].copy_(g["stage_labels"], non_blocking=True)
+            self.images, self.labels = g["static_images"], g["static_labels"]
             g["consumed"] = torch.cuda.Event(); g["consumed"].record(cur)
             g["pending"] = False
         g["student"].replay()
