@@ -246,7 +246,7 @@ def run_ours(args, rank, local_rank, world):
 
     torch.manual_seed(0)                                          # identical replicas on every rank
     margs = make_args(batch_size=BATCH_PER_GPU, pi=True, pa=True, ho=True, adv_loss_type="wgan-gp", gpu_num=world,
-                      cuda_graph=not args.no_graph)
+                      cuda_graph=not args.no_graph, allreduce_buckets=args.allreduce_buckets)
     model = NetModel(margs)
     # eval-mode BN of the frozen teacher must not be the identity
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -410,6 +410,7 @@ def main():
     ap.add_argument("--no-context", action="store_true", help="skip the torch-on-cuda context measurement (cuDNN eager on the same GPU)")
     ap.add_argument("--conv-table", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--allreduce-buckets", type=int, default=4, help="N > 1: ranges of the flat student gradient all-reduced from inside the backward pass (0: one all-reduce after it)")
     ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="3: BASELINE.json configs[2] (the metric's configuration); 4: the 360x480 batch-16 shape of configs[3]")
     args = ap.parse_args()
     select_config(args.config)

@@ -303,6 +303,26 @@ int skd_eval_upsample_accumulate(int C, int h, int w, const float* logits, long 
 int skd_eval_argmax_confusion(int H, int W, int C, const float* full, const long long* gt, long long gt_row, int valid_h, int valid_w,
                               int ignore_index, long long* confusion, unsigned char* pred, cudaStream_t);
 
+/* ---- Cityscapes training augmentation on the device (csrc/augment.cu) --------------------------------------------------------------
+   Replaces the per-sample CPU work of `CSDataSet.__getitem__` after cv2.imread (/root/reference/dataset/datasets.py:175-206):
+   id -> trainId table (:161-169), `generate_scale_label` = cv2.resize INTER_LINEAR / INTER_NEAREST by f_scale (:155-159), float32 mean
+   subtraction (:180-181), padding with 0 / ignore_label (:183-193), crop (:196-200), HWC -> CHW (:202), mirror (:203-206) -- bit-exact
+   with opencv's uint8 fixed-point resize.  The host draws the random numbers in the reference's order
+   (structure_knowledge_distillation_b200/dataset/datasets.py::draw_augmentation) and passes them here.  `samples` and `mean_bgr` are
+   HOST arrays; image / label pointers inside are DEVICE pointers to the raw decoded files (uint8 H x W x 3 BGR interleaved, uint8 H x W).
+   images: device [n][3][crop_h][crop_w] float32; labels: device [n][crop_h][crop_w], float32 (what __getitem__ returns) or int64
+   (what `NetModel.set_input` turns them into, kd_model.py:105). */
+typedef struct skd_cs_sample {
+  const unsigned char* image; const unsigned char* label;
+  int src_h, src_w;
+  double f_scale;               /* 0.7 + randint(0, 14) / 10.0; <= 0: no resize (scale=False) */
+  int scaled_h, scaled_w;       /* cvRound(src * f_scale) (ignored without resize) */
+  int h_off, w_off;             /* crop origin inside the padded, scaled image */
+  int flip;                     /* -1: mirror, +1: keep */
+} skd_cs_sample;
+int skd_cs_augment_batch(int n, const skd_cs_sample* samples, int crop_h, int crop_w, const float* mean_bgr, int ignore_label,
+                         float* images, void* labels, int labels_int64, cudaStream_t);
+
 #ifdef __cplusplus
 }
 #endif

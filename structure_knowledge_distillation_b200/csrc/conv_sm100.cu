@@ -118,7 +118,7 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (a.tma_store) ptx::prefetch_tmap(&tmap_y);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8 * PAIR); }
-    for (int s = 0; s < 2 * kResSlots; ++s) ptx::mbar_init(&res_full[s], 1);
+    for (int s = 0; s < 2 * (kResSlots + 1); ++s) ptx::mbar_init(&res_full[s], 1);
     if (a.res_prefetch) ptx::prefetch_tmap(&tmap_r);
     ptx::fence_barrier_init();
   }
@@ -278,7 +278,13 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     // will process, kResSlots - 1 chunks ahead, into the buffers of the unused pipeline stages (same 128B-swizzled layout as the
     // output staging tile).  Deep, asynchronous and issued by one thread: the epilogue warps never wait on global memory.
     uint8_t* ring = smem + a.nstages * C::kStageBytes + group * (kResSlots * C::kOutStageBytes);
-    uint64_t* rfull = res_full + group * kResSlots;
+    uint64_t* rfull = res_full + group * (kResSlots + 1);
+    // in-place mode (res_prefetch == 2): kResSlots + 1 slots per group -- the ring plus the group's staging buffer.  A slot receives the
+    // residual box (TMA load), the epilogue adds the scaled accumulator INTO it (each thread owns its pixel row: same swizzled
+    // addresses the staging write would use, no cross-thread exchange), and the TMA store reads it: one named barrier per chunk
+    // instead of three, and the next chunk never waits for the previous store to drain.
+    const int n_slots = a.res_prefetch == 2 ? kResSlots + 1 : kResSlots;
+    auto slot_ptr = [&](int slot) -> uint8_t* { return slot < kResSlots ? ring + slot * C::kOutStageBytes : stg; };
     auto chunk_valid = [&](int t, int c) -> bool {
       const int tl_ = (a.reverse ? total_tiles - 1 - t : t) / a.splits;
       const int nt_ = tl_ % a.n_tiles;
@@ -294,14 +300,15 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
       const int ty_ = rem_ / a.tiles_x, tx_ = rem_ - ty_ * a.tiles_x;
       ptx::mbar_expect_tx(&rfull[slot], C::kOutStageBytes);
-      ptx::tma_load_4d(ring + slot * C::kOutStageBytes, &tmap_r, &rfull[slot], nt_ * BLOCK_N + c * 32, tx_ * a.BW, ty_ * a.BH, img_);
+      ptx::tma_load_4d(slot_ptr(slot), &tmap_r, &rfull[slot], nt_ * BLOCK_N + c * 32, tx_ * a.BW, ty_ * a.BH, img_);
     };
     int p_tile = total_tiles, p_ch = group;                          // next chunk to request (store leader only)
     if (a.res_prefetch && is_store_leader) {
       p_tile = tile0; seek(p_tile, p_ch);
-      for (int i = 0; i < kResSlots && p_tile < total_tiles; ++i) { issue_residual(p_tile, p_ch, i); p_ch += 2; seek(p_tile, p_ch); }
+      for (int i = 0; i < n_slots && p_tile < total_tiles; ++i) { issue_residual(p_tile, p_ch, i); p_ch += 2; seek(p_tile, p_ch); }
     }
     int r_slot = 0; uint32_t r_phase = 0;                            // ring slot / parity of the chunk being consumed
+    int prev_slot = -1;                                              // in-place mode: slot whose store was committed one chunk ago
     const uint32_t tmem_empty0 = (PAIR == 2) ? ptx::mapa_shared(&tmem_empty[0], 0) : 0u;   // the leader's tmem_empty barriers
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int tu = a.reverse ? total_tiles - 1 - tile : tile;
@@ -397,6 +404,37 @@ conv_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           sq_acc += (double)part;
         }
         if (a.no_store) continue;
+        if (a.res_prefetch == 2) {                                             // CTA-uniform: accumulate into the residual slot, store from it
+          uint8_t* rs = slot_ptr(r_slot);
+          ptx::mbar_wait(&rfull[r_slot], r_phase);                             // this chunk's residual box has landed
+          uint8_t* srow = rs + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* sp4 = reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4));
+            float4 o = *sp4;
+            o.x += v[4 * j]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
+            if (a.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            else if (a.act == ACT_LEAKY) {
+              o.x = o.x < 0.f ? o.x * a.slope : o.x; o.y = o.y < 0.f ? o.y * a.slope : o.y;
+              o.z = o.z < 0.f ? o.z * a.slope : o.z; o.w = o.w < 0.f ? o.w * a.slope : o.w;
+            }
+            if (a.round_out) { o.x = ptx::round_tf32(o.x); o.y = ptx::round_tf32(o.y); o.z = ptx::round_tf32(o.z); o.w = ptx::round_tf32(o.w); }
+            *sp4 = o;
+          }
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1 + group, 128);
+          if (is_store_leader) {
+            ptx::tma_store_4d(&tmap_y, rs, c0, tx * a.BW, ty * a.BH, img);
+            ptx::bulk_commit();
+            if (prev_slot >= 0 && p_tile < total_tiles) {
+              ptx::bulk_wait_read<1>();                                        // the store committed one chunk ago has read its slot: refill it
+              issue_residual(p_tile, p_ch, prev_slot); p_ch += 2; seek(p_tile, p_ch);
+            }
+          }
+          prev_slot = r_slot;
+          if (++r_slot == kResSlots + 1) { r_slot = 0; r_phase ^= 1; }
+          continue;
+        }
         if (a.tma_store) {
           // stage the chunk in shared memory (128B-swizzled rows) and let the TMA engine write the BH x BW x 32 box:
           // fully coalesced, asynchronous, and pixels / channels outside the tensor are clipped by the hardware.
@@ -504,7 +542,7 @@ EncodeIm2colFn get_encode_im2col() {
   return fn;
 }
 int g_conv_im2col = 1;
-int g_res_prefetch = 1;
+int g_res_prefetch = 2;             // 0: residual read by the epilogue warps; 1: TMA ring + staged add; 2: TMA ring, add in place, store from the slot
 int g_tile_order = 0;             // 0 front-to-back, 1 back-to-front, 2 alternate per launch
 int g_tile_flip = 0;
 int g_k_order = 0;                // 0: by working set (channel chunks outermost when Cin >= 2048); 1: taps outermost; 2: chunks outermost
@@ -560,7 +598,8 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   constexpr int kRingBytes = 2 * kResSlots * C::kOutStageBytes;
   constexpr int kFreed = (kRingBytes + C::kStageBytes - 1) / C::kStageBytes;
   // (split precision keeps every stage for its double-size {hi, lo} tiles: a fused residual is then read coalesced by the epilogue warps)
-  a.res_prefetch = (a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && (C::kStages - kFreed >= 2) && a.passes != 3;
+  a.res_prefetch = ((a.residual != nullptr) && a.tma_store && a.vec_ok && g_res_prefetch && (C::kStages - kFreed >= 2) && a.passes != 3)
+                       ? (g_res_prefetch == 2 ? 2 : 1) : 0;
   a.nstages = a.res_prefetch ? C::kStages - kFreed : C::kStages;
   if (a.passes == 3) a.nstages = C::kStages / 2;                 // split precision: double-size stages holding the hi and lo tiles
   static bool attr = false;
@@ -592,7 +631,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
 }  // namespace
 
 extern "C" void skd_set_conv_im2col(int on) { g_conv_im2col = on ? 1 : 0; }
-extern "C" void skd_set_conv_res_prefetch(int on) { g_res_prefetch = on ? 1 : 0; }
+extern "C" void skd_set_conv_res_prefetch(int mode) { g_res_prefetch = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 extern "C" void skd_set_conv_tile_order(int mode) { g_tile_order = mode; g_tile_flip = 0; }
 extern "C" void skd_set_conv_cta_pairs(int mode) { g_cta_pairs = mode & 3; }
 extern "C" void skd_set_conv_k_order(int mode) { g_k_order = mode; }

@@ -180,24 +180,39 @@ dsn_ce_fwd_kernel(const float* __restrict__ L0, const float* __restrict__ L1, St
 // LOSS = true: the same pass also produces the loss (it has every pixel's log-sum-exp in hand): the training forward then IS the
 // backward's first phase, and the backward proper is only phase 2 -- one softmax over the 2 x 8 x 512 x 1024 upsampled pixels per
 // step instead of two (skd_dsn_ce_fwd_train / skd_dsn_ce_bwd_cols).
-template <bool LOSS>
-__global__ void __launch_bounds__(1024)
+// Round 2b: 512 threads and <= 64 registers (two blocks per SM, so one block's reduction phase overlaps the other's softmax phase);
+// the two source rows of the logits are blended ONCE per block into shared memory (row[x][c] = ly0 * L[y0][x][c] + ly1 * L[y1][x][c]),
+// so a pixel is 2 x C shared-memory reads instead of 4 x C global ones, and the softmax reuses exp(v - max) for the gradient (C
+// exponentials per pixel instead of 2 C).  CT: compile-time class bound (19 for Cityscapes; 32 generic).
+constexpr int kRowsThreads = 512;
+template <bool LOSS, int CT>
+__global__ void __launch_bounds__(kRowsThreads, 2)
 dsn_ce_bwd_rows_kernel(const float* __restrict__ L0, const float* __restrict__ L1, Strides s0, Strides s1,
                        const long long* __restrict__ labels, int N, int C, int h, int w, int H, int W, int ignore,
                        float* __restrict__ T1, int chunk, double* __restrict__ part_loss, double* __restrict__ part_cnt, float w0, float w1) {
   __shared__ double shd[32];
   double loss_acc = 0.0, cnt_acc = 0.0;
-  extern __shared__ float G[];                                 // [C][chunk|1], wa[chunk], wb[chunk], first[w+1]
+  extern __shared__ float G[];                                 // [C][chunk|1], wa[chunk], wb[chunk], first[w+2], row[w][C]
   const int pitch = chunk | 1;
   float* wa = G + (size_t)C * pitch;
   float* wb = wa + chunk;
   int* first = reinterpret_cast<int*>(wb + chunk);
+  float* row = reinterpret_cast<float*>(first + w + 2);
   const int Y = blockIdx.x, n = blockIdx.y, head = blockIdx.z;
   const float* L = head == 0 ? L0 : L1;
   const Strides st = head == 0 ? s0 : s1;
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
   const Bilin by = bilin(Y, sy, h);
   float* out = T1 + (((size_t)head * N + n) * H + Y) * (size_t)C * w;
+  {
+    const float* b0 = L + n * st.sn + (long long)by.i0 * w * st.sp;
+    const float* b1 = L + n * st.sn + (long long)by.i1 * w * st.sp;
+    for (int i = threadIdx.x; i < w * C; i += blockDim.x) {
+      const int x = i / C, c = i - x * C;
+      const long long o = (long long)x * st.sp + (long long)c * st.sc;
+      row[i] = by.l0 * __ldg(b0 + o) + by.l1 * __ldg(b1 + o);
+    }
+  }
   for (int X0 = 0; X0 < W; X0 += chunk) {
     const int X1 = min(W, X0 + chunk);
     __syncthreads();
@@ -211,19 +226,27 @@ dsn_ce_bwd_rows_kernel(const float* __restrict__ L0, const float* __restrict__ L
       wb[j] = bx.i1 == bx.i0 ? 0.f : bx.l1;
       const int prev = X == X0 ? -1 : bilin(X - 1, sx, w).i0;
       for (int x = prev + 1; x <= bx.i0; ++x) first[x] = j;     // first X of the chunk with i0 >= x
-      float v[kMaxClasses];
       if (lab == ignore) {
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) if (c < C) G[c * pitch + j] = 0.f;
+        for (int c = 0; c < CT; ++c) if (c < C) G[c * pitch + j] = 0.f;
       } else {
-        const float lse = up_logits(L, st, n, C, w, by, bx, v);
-        float pick = 0.f;
+        const float* r0 = row + bx.i0 * C;
+        const float* r1 = row + bx.i1 * C;
+        float v[CT];
+        float m = -INFINITY, pick = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) if (c < C) {
-          G[c * pitch + j] = __expf(v[c] - lse) - (c == (int)lab ? 1.f : 0.f);
+        for (int c = 0; c < CT; ++c) if (c < C) {
+          v[c] = bx.l0 * r0[c] + bx.l1 * r1[c];
+          m = fmaxf(m, v[c]);
           if (c == (int)lab) pick = v[c];
         }
-        if (LOSS) { loss_acc += (double)(lse - pick); cnt_acc += 1.0; }
+        float z = 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) if (c < C) { v[c] = __expf(v[c] - m); z += v[c]; }
+        const float rz = 1.f / z;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) if (c < C) G[c * pitch + j] = v[c] * rz - (c == (int)lab ? 1.f : 0.f);
+        if (LOSS) { loss_acc += (double)(m + __logf(z) - pick); cnt_acc += 1.0; }
       }
     }
     __syncthreads();
@@ -512,20 +535,22 @@ static int dsn_rows_launch(bool with_loss, int N, int C, int h, int w, int H, in
                            cudaStream_t st, const char* who) {
   const int heads = L1 ? 2 : 1;
   int chunk = W < 1024 ? W : 1024;
-  const size_t smem = ((size_t)C * (chunk | 1) + 2 * (size_t)chunk + (size_t)w + 2) * sizeof(float);
+  const size_t smem = ((size_t)C * (chunk | 1) + 2 * (size_t)chunk + (size_t)w + 2 + (size_t)w * C) * sizeof(float);
   if (smem > 200 * 1024) { set_error_msg(who, "source width too large for one block's shared memory"); return 0; }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel<false, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel<true, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel<false, kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dsn_ce_bwd_rows_kernel<true, kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  if (with_loss)
-    dsn_ce_bwd_rows_kernel<true><<<dim3(H, N, heads), 1024, smem, st>>>(L0, L1, a, b, labels, N, C, h, w, H, W, ignore_index, T1, chunk, part_loss,
-                                                                      part_cnt, w0, w1);
-  else
-    dsn_ce_bwd_rows_kernel<false><<<dim3(H, N, heads), 1024, smem, st>>>(L0, L1, a, b, labels, N, C, h, w, H, W, ignore_index, T1, chunk, nullptr,
-                                                                       nullptr, w0, w1);
+  const dim3 grid(H, N, heads);
+#define SKD_DSN_ROWS(LOSSF, CTV, PL, PC) \
+  dsn_ce_bwd_rows_kernel<LOSSF, CTV><<<grid, kRowsThreads, smem, st>>>(L0, L1, a, b, labels, N, C, h, w, H, W, ignore_index, T1, chunk, PL, PC, w0, w1)
+  if (with_loss) { if (C <= 19) SKD_DSN_ROWS(true, 19, part_loss, part_cnt); else SKD_DSN_ROWS(true, kMaxClasses, part_loss, part_cnt); }
+  else { if (C <= 19) SKD_DSN_ROWS(false, 19, nullptr, nullptr); else SKD_DSN_ROWS(false, kMaxClasses, nullptr, nullptr); }
+#undef SKD_DSN_ROWS
   return 1;
 }
 

@@ -98,7 +98,8 @@ class NetModel():
         self.best_mean_IU = _arg(args, "best_mean_IU", 0.0)
         if self.world > 1:
             self._sync_replicas()
-            self.G_solver.enable_overlap(_arg(args, "allreduce_buckets", 4))
+            if int(_arg(args, "allreduce_buckets", 4)) > 0:      # 0: one all-reduce after the backward pass
+                self.G_solver.enable_overlap(int(_arg(args, "allreduce_buckets", 4)))
 
         self.criterion = CriterionDSN()
         self.criterion_pixel_wise = CriterionPixelWise()

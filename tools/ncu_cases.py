@@ -22,6 +22,15 @@ def conv_case(N, Cin, H, W, Cout, k, s, p, d, halo=0, precise=False):
     return fn
 
 
+def conv1x1_case(N, Cin, H, W, Cout, res):
+    """teacher bottleneck 1x1 convolutions: folded BN (scale / shift), optional fused residual add, ReLU -- the HBM-bound launches"""
+    x = ops.to_nhwc(rn(N, Cin, H, W)); w = rn(Cout, 1, 1, Cin) / Cin ** 0.5
+    sc, sh = torch.rand(Cout, device=dev) + 0.5, rn(Cout) * 0.1
+    r = ops.to_nhwc(rn(N, Cout, H, W)) if res else None
+    out = ops.empty_nhwc(N, Cout, H, W, dev)
+    return lambda: ops.conv2d_fwd(x, w, 1, 0, 1, scale=sc, shift=sh, residual=r, act="relu", out=out)
+
+
 def wgrad_case(N, Cin, H, W, Cout, k, s, p, d):
     x = ops.to_nhwc(rn(N, Cin, H, W))
     oh, ow = ops.conv_out_hw(H, W, (k, k), s, p, d)
@@ -52,13 +61,32 @@ CASES = {
     "conv64_3x_general": lambda: conv_case(8, 64, 256, 512, 64, 3, 1, 1, 1, halo=0, precise=True),
     "conv64_3x_halo": lambda: conv_case(8, 64, 256, 512, 64, 3, 1, 1, 1, halo=1, precise=True),
     "conv128_64_halo": lambda: conv_case(8, 128, 256, 512, 64, 3, 1, 1, 1, halo=1),
+    "conv1x1_256_1024_res": lambda: conv1x1_case(8, 256, 65, 129, 1024, True),
+    "conv1x1_1024_256": lambda: conv1x1_case(8, 1024, 65, 129, 256, False),
+    "conv1x1_512_2048_res": lambda: conv1x1_case(8, 512, 65, 129, 2048, True),
     "abn_stats_stem": lambda: abn_case(8, 64, 256, 512, "stats"),
     "abn_apply_stem": lambda: abn_case(8, 64, 256, 512, "apply"),
     "abn_bwd_stem": lambda: abn_case(8, 64, 256, 512, "bwd"),
     "abn_bwd_res_l1": lambda: abn_case(8, 64, 129, 257, "bwd", res=True),
 }
 
+def time_case(name, iters=20):
+    fn = CASES[name]()
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "--time":                                  # CUDA-event timings (us) instead of a profiler range
+        for name in sys.argv[2:]:
+            print("%-28s %8.1f us" % (name, time_case(name)))
+        sys.exit(0)
     for name in sys.argv[1:]:
         fn = CASES[name]()
         for _ in range(2):
