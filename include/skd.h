@@ -214,6 +214,14 @@ int skd_slice_copy(long long rows, int C, const float* src, int src_pitch, int s
 /* G_solver.step (networks/kd_model.py:74,171): v = mu*v + (g*grad_scale + wd*p); p -= lr*v; lr read from device memory */
 int skd_sgd_step(long long n, float* param, const float* grad, float* momentum_buf, const float* lr, float momentum,
                  float weight_decay, int first_step, float grad_scale, cudaStream_t);
+/* The same update fused with the data-parallel gradient exchange over NVSwitch multicast (replaces Reduce.apply + the per-GPU
+   optimizer of utils/parallel.py:54-63,155 + kd_model.py:171): the calling rank owns elements [lo, hi) of the flat buffers (multiples of
+   4): g = multimem.ld_reduce.add over every rank's gradient (summed inside the switch), momentum-SGD with grad_scale = 1/world, new
+   parameters multimem.st-broadcast to every rank.  param_mc / grad_mc: MULTICAST addresses of the symmetric parameter / gradient
+   buffers (element 0); param_local: this rank's own copy; momentum_buf: local, only [lo, hi) is used.  The caller brackets the call
+   with two cross-rank barriers (gradients complete before, parameters complete after). */
+int skd_sgd_step_nvls(long long lo, long long hi, float* param_mc, const float* grad_mc, const float* param_local, float* momentum_buf,
+                      const float* lr, float momentum, float weight_decay, float grad_scale, cudaStream_t);
 
 
 /* ---- F. SAGAN discriminator of the holistic loss (networks/sagan_models.py:9-41,105-168, networks/spectral.py:23-35) and the

@@ -319,6 +319,40 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
   }
 }
 
+// ---- data-parallel SGD over NVSwitch multicast ------------------------------------------------------------------------------
+// The gradient exchange of the path (utils/parallel.py:54-63,155: mean over GPUs of per-GPU gradients) fused with the optimizer:
+// rank r owns a contiguous range of the flat buffers.  For every float4 of its range it issues ONE multimem.ld_reduce on the
+// multicast address of the symmetric gradient buffer -- the NVSwitch fetches that float4 from every GPU and adds them in the
+// switch (NVLS), so the sum arrives over this GPU's links once instead of world-1 times -- applies momentum-SGD with 1/world folded
+// in, and writes the new parameters with ONE multimem.st on the multicast address of the symmetric parameter buffer, which the
+// switch replicates into every GPU's copy.  A reduce-scatter, the update and an all-gather in a single pass; the momentum buffer
+// is touched only by the owner (1/world of the optimizer traffic per GPU); every replica receives bit-identical parameters.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__global__ void __launch_bounds__(256)
+sgd_nvls_kernel(long long lo4, long long hi4, float* __restrict__ p_mc, const float* __restrict__ g_mc, const float* __restrict__ p_local,
+                float* __restrict__ v, const float* __restrict__ lr_ptr, float momentum, float wd, float gscale) {
+  const float lr = __ldg(lr_ptr);
+  for (long long i = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 gg = multimem_ld_reduce_add(g_mc + 4 * i);
+    float4 pp = reinterpret_cast<const float4*>(p_local)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define UPD(f) { const float d = gg.f * gscale + wd * pp.f; vv.f = momentum * vv.f + d; pp.f -= lr * vv.f; }
+    UPD(x) UPD(y) UPD(z) UPD(w)
+#undef UPD
+    reinterpret_cast<float4*>(v)[i] = vv;
+    multimem_st(p_mc + 4 * i, pp);
+  }
+  __threadfence_system();
+}
+
 Pyramid make_pyramid(int levels, const int* sizes) {
   Pyramid p; p.levels = levels; p.first_bin[0] = 0;
   for (int i = 0; i < 4; ++i) p.size[i] = i < levels ? sizes[i] : 1;
@@ -434,4 +468,19 @@ extern "C" int skd_sgd_step(long long n, float* param, const float* grad, float*
   const long long n4 = al ? n / 4 : 0;
   sgd_kernel<<<ew_blocks(n / 4 + 1), 256, 0, st>>>(param, grad, momentum_buf, n4, n, lr, momentum, weight_decay, first_step, grad_scale);
   return finish("skd_sgd_step");
+}
+
+extern "C" int skd_sgd_step_nvls(long long lo, long long hi, float* param_mc, const float* grad_mc, const float* param_local, float* momentum_buf,
+                                 const float* lr, float momentum, float weight_decay, float grad_scale, cudaStream_t st) {
+  const char* who = "skd_sgd_step_nvls";
+  if (hi <= lo) return 1;
+  if ((lo | hi) & 3 || ((reinterpret_cast<uintptr_t>(param_mc) | reinterpret_cast<uintptr_t>(grad_mc) | reinterpret_cast<uintptr_t>(param_local) |
+                         reinterpret_cast<uintptr_t>(momentum_buf)) & 15) || !param_mc || !grad_mc) {
+    set_error_msg(who, "range bounds must be multiples of 4 floats, buffers 16-byte aligned, multicast addresses non-null"); return 0;
+  }
+  const long long n4 = (hi - lo) / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  sgd_nvls_kernel<<<(int)blocks, 256, 0, st>>>(lo / 4, hi / 4, param_mc, grad_mc, param_local, momentum_buf, lr, momentum, weight_decay, grad_scale);
+  return finish(who);
 }

@@ -91,14 +91,23 @@ class NetModel():
         self.D_model = D_model.float().to(device).train()
         self.parallel_D = self.D_model
 
+        # gradient exchange for world > 1: "nccl" = bucketed ncclAllReduce issued from inside the backward pass (default);
+        # "nvls" = no NCCL on the path: the reduction happens inside the SGD kernel over NVSwitch multicast (FlatSGD.step_nvls)
+        self.allreduce = str(_arg(args, "allreduce", "nccl")) if self.world > 1 else "none"
+        if self.allreduce not in ("nccl", "nvls", "none"):
+            raise ValueError("allreduce must be 'nccl' or 'nvls'")
+        sym = self.allreduce == "nvls"
         self.G_solver = FlatSGD([p for p in self.student.parameters() if p.requires_grad], args.lr_g, momentum=args.momentum,
-                                weight_decay=args.weight_decay, direct_grads=True)
+                                weight_decay=args.weight_decay, direct_grads=True, symmetric=sym)
         self.D_solver = FlatSGD([p for p in self.D_model.parameters() if p.requires_grad], args.lr_d, momentum=args.momentum,
-                                weight_decay=args.weight_decay)
+                                weight_decay=args.weight_decay, symmetric=sym)
         self.best_mean_IU = _arg(args, "best_mean_IU", 0.0)
         if self.world > 1:
             self._sync_replicas()
-            if int(_arg(args, "allreduce_buckets", 4)) > 0:      # 0: one all-reduce after the backward pass
+            if sym:
+                self.G_solver.enable_nvls()
+                self.D_solver.enable_nvls()
+            elif int(_arg(args, "allreduce_buckets", 4)) > 0:      # 0: one all-reduce after the backward pass
                 self.G_solver.enable_overlap(int(_arg(args, "allreduce_buckets", 4)))
 
         self.criterion = CriterionDSN()
@@ -292,7 +301,7 @@ class NetModel():
 
     def _updates(self):
         """G_solver.step() and, with Ho, the D all-reduce + D_solver.step() (kd_model.py:171, :165)."""
-        self._reduce_G()
+        self._reduce_G()                                     # no-ops with allreduce == "nvls": FlatSGD.step() reduces inside its kernel
         self.G_solver.step()
         if self.args.ho == True:
             self.D_solver.all_reduce_grads(self.world)

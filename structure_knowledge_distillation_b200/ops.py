@@ -529,5 +529,11 @@ def pairwise_affinity_bwd_sm100(E, pS, rS, arg, grad_out, feat_like):
     return dF
 
 
+def sgd_step_nvls(lo, hi, param_mc, grad_mc, param_local, buf, lr_dev, momentum, weight_decay, grad_scale):
+    """data-parallel SGD over NVSwitch multicast on the owned range [lo, hi): see include/skd.h skd_sgd_step_nvls"""
+    lib().skd_sgd_step_nvls(int(lo), int(hi), int(param_mc), int(grad_mc), _p(param_local), _p(buf), _p(lr_dev), momentum, weight_decay,
+                            grad_scale, _st())
+
+
 def sgd_step(param, grad, buf, lr_dev, momentum, weight_decay, first, grad_scale=1.0):
     lib().skd_sgd_step(param.numel(), _p(param), _p(grad), _p(buf), _p(lr_dev), momentum, weight_decay, int(first), grad_scale, _st())

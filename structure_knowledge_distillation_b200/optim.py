@@ -25,11 +25,14 @@ def _dense(t):
 
 
 class FlatSGD:
-    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, direct_grads=False):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, direct_grads=False, symmetric=False):
         """direct_grads: the backward kernels of functions.py write each parameter's gradient straight into its view of the flat
         buffer (`p._skd_grad`) instead of returning a tensor for autograd to add -- one elementwise launch and one temporary less
         per parameter.  Valid because zero_grad() precedes every backward and no parameter is used twice in one forward; a caller
-        that accumulates several backward passes into .grad must leave it off."""
+        that accumulates several backward passes into .grad must leave it off.
+        symmetric: allocate the flat parameter and gradient buffers in torch symmetric memory (same virtual layout on every rank,
+        NVSwitch multicast mapping) -- the precondition of `enable_nvls()`.  Collective: every rank must construct its optimizers
+        in the same order."""
         self.params = [p for p in params]
         if not self.params:
             raise ValueError("optimizer got an empty parameter list")
@@ -39,8 +42,14 @@ class FlatSGD:
         for p in self.params:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4                       # keep every tensor 16-byte aligned
-        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self._nvls = None
+        if symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.flat_p = symm_mem.empty(total, dtype=torch.float32, device=dev); self.flat_p.zero_()
+            self.flat_g = symm_mem.empty(total, dtype=torch.float32, device=dev); self.flat_g.zero_()
+        else:
+            self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
+            self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
         self._views = []
         for p, off in zip(self.params, offs):
@@ -70,11 +79,44 @@ class FlatSGD:
 
     def all_reduce_grads(self, world):
         """utils/parallel.py:54-63,155 semantics: mean over ranks of per-rank gradients."""
+        if self._nvls is not None:                                   # the reduction happens inside step_nvls()
+            return
         if world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
             self.grad_scale = 1.0 / world
         else:
             self.grad_scale = 1.0
+
+    # ---- gradient exchange fused into the update: NVSwitch multicast (multimem.ld_reduce / multimem.st) -----------------------------
+    def enable_nvls(self, group=None):
+        """Rendezvous of the symmetric flat buffers (collective).  Afterwards `step_nvls()` replaces all-reduce + step: this rank
+        updates elements [lo, hi) -- 1/world of the parameters -- from the switch-reduced gradient and multicasts the result.
+        Raises when the buffers are not symmetric or the fabric has no multicast support (caller falls back to NCCL)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        hp = symm_mem.rendezvous(self.flat_p, group)
+        hg = symm_mem.rendezvous(self.flat_g, group)
+        if not hp.multicast_ptr or not hg.multicast_ptr:
+            raise RuntimeError("symmetric memory without multicast (NVLS) support on this system")
+        world, rank = hp.world_size, hp.rank
+        n4 = self._offsets[-1] // 4
+        per = (n4 + world - 1) // world
+        lo4, hi4 = min(rank * per, n4), min((rank + 1) * per, n4)
+        self._nvls = dict(hp=hp, hg=hg, lo=4 * lo4, hi=4 * hi4, world=world, rank=rank)
+        self.grad_scale = 1.0 / world
+
+    def step_nvls(self):
+        """barrier | ld_reduce(grad) -> SGD on the owned range -> multicast store(param) | barrier, on the current stream (capturable).
+        The first barrier orders every rank's gradient writes before any rank's reduction; the second keeps every rank from reading
+        parameters -- or zeroing gradients -- before all ranges have been reduced and broadcast."""
+        nv = self._nvls
+        g = self.param_groups[0]
+        self.lr_dev.fill_(float(g['lr']))
+        nv["hg"].barrier(channel=0)
+        ops.sgd_step_nvls(nv["lo"], nv["hi"], nv["hp"].multicast_ptr, nv["hg"].multicast_ptr, self.flat_p, self.flat_m, self.lr_dev,
+                          g['momentum'], g['weight_decay'], 1.0 / nv["world"])
+        nv["hp"].barrier(channel=1)
+        self.steps += 1
 
     # ---- all-reduce overlapped with the backward pass -------------------------------------------------------------------------
     def enable_overlap(self, n_buckets=4):
@@ -147,6 +189,8 @@ class FlatSGD:
         self._active = False
 
     def step(self):
+        if self._nvls is not None:
+            return self.step_nvls()
         g = self.param_groups[0]
         self.lr_dev.fill_(float(g['lr']))
         # momentum buffer starts at zero, so the first step needs no special case (v = mu*0 + d)
@@ -154,7 +198,11 @@ class FlatSGD:
         self.steps += 1
 
     def state_dict(self):
-        return dict(momentum=self.flat_m.clone(), steps=self.steps, lr=self.param_groups[0]['lr'])
+        m = self.flat_m.clone()
+        if self._nvls is not None:                                   # each rank holds the momentum of its own range only (zeros elsewhere)
+            m[:self._nvls["lo"]] = 0; m[self._nvls["hi"]:] = 0
+            dist.all_reduce(m, op=dist.ReduceOp.SUM)
+        return dict(momentum=m, steps=self.steps, lr=self.param_groups[0]['lr'])
 
     def load_state_dict(self, sd):
         self.flat_m.copy_(sd['momentum']); self.steps = sd['steps']; self.param_groups[0]['lr'] = sd['lr']

@@ -142,3 +142,81 @@ def test_sync_bn_two_ranks_equals_full_batch():
     res = q.get(timeout=30)
     assert res[0] == "ok", res
     print("\nPARITY sync_bn_world2", res[1])
+
+
+def _nvls_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        from structure_knowledge_distillation_b200.optim import FlatSGD
+        # ---- optimizer level: ragged parameter list, two steps (momentum), against the explicit formula on gathered gradients
+        gen = torch.Generator().manual_seed(3)
+        shapes = [(64, 3, 3, 3), (64,), (19, 128, 1, 1), (7,), (513, 33), (1,)]
+        init = [torch.randn(s, generator=gen) for s in shapes]
+        params = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+        opt = FlatSGD(params, 0.05, momentum=0.9, weight_decay=5e-4, symmetric=True)
+        opt.enable_nvls()
+        p_ref = opt.flat_p.clone(); m_ref = torch.zeros_like(p_ref)
+        worst = 0.0
+        for step in range(2):
+            opt.zero_grad()
+            g_local = torch.randn(opt.flat_g.shape, generator=torch.Generator().manual_seed(50 + 10 * step + rank)).cuda()
+            opt.flat_g.copy_(g_local)
+            parts = [torch.empty_like(g_local) for _ in range(world)]
+            dist.all_gather(parts, g_local)
+            d = sum(parts) / world + 5e-4 * p_ref
+            m_ref = 0.9 * m_ref + d
+            p_ref = p_ref - 0.05 * m_ref
+            opt.step()                                                   # dispatches to step_nvls(): barrier | ld_reduce + SGD + multicast | barrier
+            torch.cuda.synchronize()
+            worst = max(worst, float((opt.flat_p - p_ref).abs().max() / p_ref.abs().max()))
+            allp = [torch.empty_like(p_ref) for _ in range(world)]
+            dist.all_gather(allp, opt.flat_p.clone())
+            assert all(torch.equal(a, allp[0]) for a in allp), "replicas differ after the multicast store"
+        assert worst < 1e-6, worst
+        assert torch.equal(params[4].data, opt.flat_p[opt._offsets[4]:opt._offsets[4] + 513 * 33].view(513, 33))   # parameters are views
+        sd = opt.state_dict()                                            # momentum is sharded: state_dict() reassembles it
+        assert float((sd["momentum"] - m_ref).abs().max() / m_ref.abs().max()) < 1e-6
+        # ---- model level: one distillation step with the fused exchange == the same step with NCCL all-reduce + SGD
+        from oracle import port as oport
+        from structure_knowledge_distillation_b200.networks.kd_model import NetModel
+        from structure_knowledge_distillation_b200.utils.train_options import make_args
+        res = {}
+        for mode in ("nccl", "nvls"):
+            torch.manual_seed(100)
+            m = NetModel(make_args(batch_size=1, pi=True, pa=True, ho=True, adv_loss_type="hinge", gpu_num=world, allreduce=mode))
+            images, labels = oport.synthetic_batch(1, 512, 512, seed=7 + rank)
+            m.set_input((images, labels, None, None))
+            for drop in m.student.dropouts():
+                drop.injected = (torch.rand(1, 128, generator=torch.Generator().manual_seed(5 + rank)) >= 0.1).float()
+            m.optimize_parameters()
+            torch.cuda.synchronize()
+            res[mode] = (m.G_solver.flat_p.clone(), m.D_solver.flat_p.clone())
+            del m
+        eg = float((res["nvls"][0] - res["nccl"][0]).abs().max() / res["nccl"][0].abs().max())
+        ed = float((res["nvls"][1] - res["nccl"][1]).abs().max() / res["nccl"][1].abs().max())
+        assert eg < 1e-5 and ed < 1e-5, (eg, ed)
+        if rank == 0:
+            out.put(("ok", dict(optimizer=worst, model_G=eg, model_D=ed)))
+    except Exception as e:                                              # noqa: BLE001
+        out.put(("fail", rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nvls_fused_sgd_two_ranks():
+    """Gradient exchange fused into the SGD kernel over NVSwitch multicast (skd_sgd_step_nvls: multimem.ld_reduce + multimem.st):
+    equals p - lr * (mu * v + mean_over_ranks(g) + wd * p) over two steps, replicas bit-identical, and a whole distillation step equals
+    the NCCL path's."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    mp.spawn(_nvls_worker, args=(2, 29591, q), nprocs=2, join=True)
+    res = q.get(timeout=30)
+    assert res[0] == "ok", res
+    print("\nPARITY nvls_fused_sgd_world2", res[1])
