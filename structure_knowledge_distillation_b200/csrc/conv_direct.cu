@@ -108,8 +108,12 @@ colsum_kernel(const float* __restrict__ dy, int ldy, long long P, int C, float* 
 // Explicit im2col for tiny-Cin convolutions (the 3-channel stem): col[p][(kh*KW+kw)*Cin + ci], zero padded to Kp columns.
 // With K = 27 a tensor-core implicit GEMM would spend 9 mostly-empty K steps per tile; one dense 32-wide K step on this
 // matrix (134 MB at batch 8) is 5x cheaper, and the weight gradient becomes a single-tap GEMM over the same matrix.
+// CIN / KHW > 0: compile-time channel count and (square) filter size -- the index arithmetic (six divisions per element) folds into
+// multiplies; 0: run-time values.  The stem convolution (3 channels, 3x3) is the only caller on the path.
+template <int CIN, int KHW>
 __global__ void __launch_bounds__(256)
 im2col_small_kernel(Geo g, const float* __restrict__ x, int ldx, float* __restrict__ col, int Kp) {
+  if (CIN > 0) { g.Cin = CIN; g.KH = KHW; g.KW = KHW; }
   const long long total = (long long)g.N * g.OH * g.OW * (Kp / 4);
   const int K = g.KH * g.KW * g.Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -190,6 +194,8 @@ extern "C" int skd_im2col_small(int N, int H, int W, int Cin, int KH, int KW, in
                                 float* col, int Kp, cudaStream_t st) {
   if (Kp % 4 || Kp < KH * KW * Cin) { set_error_msg("skd_im2col_small", "Kp must be a multiple of 4 and >= KH*KW*Cin"); return 0; }
   const Geo g = make_geo(N, H, W, Cin, 1, KH, KW, stride, pad, dil);
-  im2col_small_kernel<<<ew_blocks((long long)N * g.OH * g.OW * (Kp / 4)), 256, 0, st>>>(g, x, ldx, col, Kp);
+  const int blocks = ew_blocks((long long)N * g.OH * g.OW * (Kp / 4));
+  if (Cin == 3 && KH == 3 && KW == 3) im2col_small_kernel<3, 3><<<blocks, 256, 0, st>>>(g, x, ldx, col, Kp);
+  else im2col_small_kernel<0, 0><<<blocks, 256, 0, st>>>(g, x, ldx, col, Kp);
   return finish("skd_im2col_small");
 }
