@@ -5,7 +5,7 @@ SO=${1:-structure_knowledge_distillation_b200/libskd_b200.so}
 TMP=$(mktemp)
 cuobjdump -sass "$SO" > "$TMP"
 echo "# cuobjdump -sass $SO : opcode histogram (whole library)"
-grep -oE 'UTC[A-Z0-9.]*MMA[A-Z0-9.]*|LDTM[A-Z0-9.]*|STTM[A-Z0-9.]*|UTMA[A-Z0-9.]*|UTCBAR[A-Z0-9.]*|UTCCP[A-Z0-9.]*|SYNCS[A-Z0-9.]*|UBLKCP[A-Z0-9.]*|HMMA[A-Z0-9.]*' "$TMP" | sort | uniq -c | sort -rn
+grep -oE 'UTC[A-Z0-9.]*MMA[A-Z0-9.]*|LDTM[A-Z0-9.]*|STTM[A-Z0-9.]*|UTMA[A-Z0-9.]*|UTCBAR[A-Z0-9.]*|UTCCP[A-Z0-9.]*|SYNCS[A-Z0-9.]*|UBLKCP[A-Z0-9.]*|HMMA[A-Z0-9.]*|LDGMC[A-Z0-9.]*|STG[A-Z0-9.]*MC[A-Z0-9.]*|REDG?MC[A-Z0-9.]*' "$TMP" | sort | uniq -c | sort -rn
 echo
 echo "# per kernel: UTCHMMA / LDTM / UTMALDG / UTMASTG counts (kernels with at least one)"
 awk '/Function :/ {name=$3} /UTCHMMA/ {m[name]++} /LDTM/ {l[name]++} /UTMALDG/ {t[name]++} /UTMASTG/ {s[name]++}
