@@ -24,6 +24,14 @@ def _dense(t):
     return True
 
 
+def owned_range(total, world, rank):
+    """[lo, hi) of a flat buffer of `total` floats (a multiple of 4) that `rank` reduces, updates and multicasts in step_nvls():
+    contiguous, float4-aligned, the ranges of all ranks tile [0, total) exactly."""
+    n4 = total // 4
+    per = (n4 + world - 1) // world
+    return 4 * min(rank * per, n4), 4 * min((rank + 1) * per, n4)
+
+
 class FlatSGD:
     def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, direct_grads=False, symmetric=False):
         """direct_grads: the backward kernels of functions.py write each parameter's gradient straight into its view of the flat
@@ -92,17 +100,20 @@ class FlatSGD:
         """Rendezvous of the symmetric flat buffers (collective).  Afterwards `step_nvls()` replaces all-reduce + step: this rank
         updates elements [lo, hi) -- 1/world of the parameters -- from the switch-reduced gradient and multicasts the result.
         Raises when the buffers are not symmetric or the fabric has no multicast support (caller falls back to NCCL)."""
+        import os
         import torch.distributed._symmetric_memory as symm_mem
         group = dist.group.WORLD if group is None else group
+        if dist.get_world_size(group) > 2 and os.environ.get("SKD_NVLS_ANY_WORLD") != "1":
+            # validated on hardware for 2 ranks only (tests/test_ddp_nccl_gpu.py); the one 4-rank run of this round did not finish
+            # (DESIGN.md section 5).  Fail here, loudly, rather than risk a cross-rank hang inside a training job.
+            raise RuntimeError("allreduce='nvls' is validated for world_size 2 only; use allreduce='nccl' (or set SKD_NVLS_ANY_WORLD=1 to try)")
         hp = symm_mem.rendezvous(self.flat_p, group)
         hg = symm_mem.rendezvous(self.flat_g, group)
         if not hp.multicast_ptr or not hg.multicast_ptr:
             raise RuntimeError("symmetric memory without multicast (NVLS) support on this system")
         world, rank = hp.world_size, hp.rank
-        n4 = self._offsets[-1] // 4
-        per = (n4 + world - 1) // world
-        lo4, hi4 = min(rank * per, n4), min((rank + 1) * per, n4)
-        self._nvls = dict(hp=hp, hg=hg, lo=4 * lo4, hi=4 * hi4, world=world, rank=rank)
+        lo, hi = owned_range(self._offsets[-1], world, rank)
+        self._nvls = dict(hp=hp, hg=hg, lo=lo, hi=hi, world=world, rank=rank)
         self.grad_scale = 1.0 / world
 
     def step_nvls(self):

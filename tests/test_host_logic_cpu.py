@@ -173,3 +173,14 @@ def test_checkpoint_loaders_follow_reference_semantics(tmp_path):
     assert U.load_T_model(dst3, str(tmp_path / "teacher.pth"))
     assert torch.equal(dst3.state_dict()["pspmodule.bottleneck.0.weight"], src.state_dict()["pspmodule.bottleneck.0.weight"])
     assert not U.load_T_model(dst3, str(tmp_path / "missing.pth"))
+
+
+def test_nvls_owned_ranges_tile_the_flat_buffer():
+    """FlatSGD.step_nvls(): every float of the flat buffer is reduced / updated / multicast by exactly one rank, on float4 boundaries."""
+    from structure_knowledge_distillation_b200.optim import owned_range
+    for total in (4, 8, 52, 13_071_236, 3_200_004):
+        for world in (1, 2, 3, 4, 8):
+            edges = [owned_range(total, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            for (lo, hi), (lo2, _) in zip(edges, edges[1:] + [(total, total)]):
+                assert lo % 4 == 0 and hi % 4 == 0 and lo <= hi and hi == lo2
