@@ -180,6 +180,7 @@ int skd_conv2d_dgrad_direct(int N, int H, int W, int Cin, int Cout, int KH, int 
 int skd_conv2d_wgrad_direct(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, const float* x,
                             int ldx, const float* dy, int ldy, float* dw, cudaStream_t);
 int skd_colsum(long long P, int C, const float* dy, int ldy, float* db, cudaStream_t);
+int skd_colsum_acc(long long P, int C, const float* dy, int ldy, float* db, cudaStream_t);   /* db += (bias gradients accumulated over passes) */
 /* explicit im2col for tiny-Cin convolutions (3-channel stem): col[N*OH*OW][Kp], k = (kh*KW+kw)*Cin+ci, zero padded to Kp */
 int skd_im2col_small(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int dil, const float* x, int ldx, float* col,
                      int Kp, cudaStream_t);

@@ -180,8 +180,8 @@ extern "C" int skd_conv2d_wgrad_direct(int N, int H, int W, int Cin, int Cout, i
   return finish("skd_conv2d_wgrad_direct");
 }
 
-extern "C" int skd_colsum(long long P, int C, const float* dy, int ldy, float* db, cudaStream_t st) {
-  if (cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), st) != cudaSuccess) return finish("skd_colsum(memset)");
+static int colsum_launch(long long P, int C, const float* dy, int ldy, float* db, bool accumulate, cudaStream_t st) {
+  if (!accumulate && cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), st) != cudaSuccess) return finish("skd_colsum(memset)");
   const int bx = (C + 31) / 32;
   long long split = (4LL * kNumSMs + bx - 1) / bx;
   if (split > (P + 63) / 64) split = (P + 63) / 64;
@@ -189,6 +189,9 @@ extern "C" int skd_colsum(long long P, int C, const float* dy, int ldy, float* d
   colsum_kernel<<<dim3(bx, (unsigned)split), 256, 0, st>>>(dy, ldy, P, C, db);
   return finish("skd_colsum");
 }
+extern "C" int skd_colsum(long long P, int C, const float* dy, int ldy, float* db, cudaStream_t st) { return colsum_launch(P, C, dy, ldy, db, false, st); }
+// db += column sums (the bias gradient of the second and third discriminator pass of a phase accumulates in place)
+extern "C" int skd_colsum_acc(long long P, int C, const float* dy, int ldy, float* db, cudaStream_t st) { return colsum_launch(P, C, dy, ldy, db, true, st); }
 
 extern "C" int skd_im2col_small(int N, int H, int W, int Cin, int KH, int KW, int stride, int pad, int dil, const float* x, int ldx,
                                 float* col, int Kp, cudaStream_t st) {

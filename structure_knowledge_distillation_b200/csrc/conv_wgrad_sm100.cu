@@ -29,7 +29,11 @@ struct WgArgs {
   int m_tiles, n_tiles, taps, splits, kb_total, kb_per_split;
   float* ws;                               // [splits][Cout][taps*Cin]
   int linear;                              // K-blocks are 32 consecutive output pixels (dY as a [P][Cout] matrix, X through TMA im2col)
+  // pipeline geometry (run time): with Cout <= 64 the dY operand needs two of its four 32-channel chunks, the stage shrinks and a
+  // third / fourth stage fits (the M = 128 MMA then reads x data as rows 64..127 of A: finite garbage in accumulator rows nobody stores)
+  int a_bytes, stage_bytes, nstages;
 };
+constexpr int kMaxStages = 4;
 
 // PAIR = 2: a cluster of two CTAs (cta_group::2) owns a 256 (Cout) x BLOCK_N (Cin) tile: each CTA stages its own 128 Cout rows of dY
 // and only HALF of the x tile (BLOCK_N / 2 channels), the leader issues M = 256 MMAs.  Per 128 x BLOCK_N of MMA work a CTA then moves
@@ -56,8 +60,8 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-  uint64_t* empty_bar = full_bar + C::kStages;
-  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,7 +71,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_dy); ptx::prefetch_tmap(&tmap_x);
-    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < a.nstages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4 * PAIR); }
     ptx::fence_barrier_init();
   }
@@ -106,8 +110,8 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
         const int b_chunks = max(0, min(BLOCK_N / 32 / PAIR, (a.Cin - n0 + 31) / 32));
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + C::kABytes;
+          uint8_t* sa = smem + stage * a.stage_bytes;
+          uint8_t* sb = sa + a.a_bytes;
           if constexpr (PAIR == 2) {
             // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both (the peer's chunk counts are its own:
             // Cout % 256 == 0 makes a_chunks 4 in both; the peer's share of x may be ragged)
@@ -124,7 +128,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
             for (int c = 0; c < b_chunks; ++c)
               ptx::tma_load_im2col_4d_2cta(sb + c * C::kChunkBytes, &tmap_x, fb, n0 + c * 32, ox * a.stride - a.pad, oy * a.stride - a.pad, img,
                                            (uint16_t)(kw * a.dil), (uint16_t)(kh * a.dil));
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            if (++stage == a.nstages) { stage = 0; phase ^= 1; }
             continue;
           }
           ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)((a_chunks + b_chunks) * C::kChunkBytes));
@@ -147,7 +151,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
               ptx::tma_load_4d(sb + c * C::kChunkBytes, &tmap_x, &full_bar[stage], nt * BLOCK_N + c * 32,
                                ox0 * a.stride - a.pad + kw * a.dil, oy0 * a.stride - a.pad + kh * a.dil, img);
           }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == a.nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -166,8 +170,8 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
         if (lane == 0) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t sb = sa + C::kABytes;
+          const uint32_t sa = ptx::smem_u32(smem + stage * a.stage_bytes);
+          const uint32_t sb = sa + (uint32_t)a.a_bytes;
 #pragma unroll
           for (int kk = 0; kk < C::kKPix / 8; ++kk) {
             // MN-major tf32 must use the 128B swizzle with 32B atoms (UMMA layout type 1 <-> TMA SWIZZLE_128B_ATOM_32B):
@@ -186,7 +190,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __gri
           }
         }
         __syncwarp();
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == a.nstages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -324,8 +328,16 @@ Plan make_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int strid
 }
 
 template <int BLOCK_N, int PAIR>
-int launch(const CUtensorMap& tdy, const CUtensorMap& tx, const WgArgs& a, int units, cudaStream_t st) {
+int launch(const CUtensorMap& tdy, const CUtensorMap& tx, const WgArgs& a_in, int units, cudaStream_t st) {
   using C = WCfg<BLOCK_N, PAIR>;
+  WgArgs a = a_in;
+  const int a_chunks_max = (PAIR == 2 || a.Cout > 96) ? 4 : (a.Cout > 64 ? 3 : (a.Cout > 32 ? 2 : 1));
+  a.a_bytes = (PAIR == 2) ? C::kABytes : ((a_chunks_max * C::kChunkBytes + 1023) / 1024) * 1024;
+  a.stage_bytes = a.a_bytes + C::kBBytes;
+  a.nstages = (C::kStages * C::kStageBytes) / a.stage_bytes;
+  if (a.nstages > kMaxStages) a.nstages = kMaxStages;
+  // the M = 128 MMA always reads four A chunks: the last stage's must stay inside the data region
+  while (a.nstages > 1 && (a.nstages - 1) * a.stage_bytes + C::kABytes > C::kStages * C::kStageBytes) --a.nstages;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_sm100_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);

@@ -308,9 +308,7 @@ class DiscEngine:
                 m = lay["m"]
                 db, acc = self._grad_buf(sink, names[li] + ".bias", m.bias)
                 if acc:
-                    tmp = _f(cout, dev=dev)
-                    L.skd_colsum(B * oh * ow, cout, _p(g), cout, _p(tmp), st)
-                    db.add_(tmp)
+                    L.skd_colsum_acc(B * oh * ow, cout, _p(g), cout, _p(db), st)
                 else:
                     L.skd_colsum(B * oh * ow, cout, _p(g), cout, _p(db), st)
                 dwn = _f(cout, 16, cin_p, dev=dev)
