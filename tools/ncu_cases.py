@@ -31,6 +31,22 @@ def conv1x1_case(N, Cin, H, W, Cout, res):
     return lambda: ops.conv2d_fwd(x, w, 1, 0, 1, scale=sc, shift=sh, residual=r, act="relu", out=out)
 
 
+def dsn_case():
+    l0 = ops.to_nhwc(rn(8, 19, 65, 129)); l1 = ops.to_nhwc(rn(8, 19, 65, 129))
+    lab = torch.randint(0, 19, (8, 512, 1024), device=dev); lab[torch.rand(8, 512, 1024, device=dev) < 0.05] = 255
+    return lambda: ops.dsn_ce_fwd_train(l0, l1, lab, 255, 1.0, 0.4)
+
+
+def augment_case():
+    from structure_knowledge_distillation_b200.dataset.datasets import DeviceAugment, draw_augmentation
+    import random, numpy as np
+    random.seed(0); np.random.seed(0)
+    img = torch.randint(0, 256, (8, 1024, 2048, 3), dtype=torch.uint8, device=dev); lab = torch.randint(0, 34, (8, 1024, 2048), dtype=torch.uint8, device=dev)
+    augs = torch.tensor([draw_augmentation(1024, 2048, (512, 1024)) for _ in range(8)], dtype=torch.float64)
+    aug = DeviceAugment((512, 1024), (104.00698793, 116.66876762, 122.67891434))
+    return lambda: aug(img, lab, augs)
+
+
 def wgrad_case(N, Cin, H, W, Cout, k, s, p, d):
     x = ops.to_nhwc(rn(N, Cin, H, W))
     oh, ow = ops.conv_out_hw(H, W, (k, k), s, p, d)
@@ -64,6 +80,8 @@ CASES = {
     "conv1x1_256_1024_res": lambda: conv1x1_case(8, 256, 65, 129, 1024, True),
     "conv1x1_1024_256": lambda: conv1x1_case(8, 1024, 65, 129, 256, False),
     "conv1x1_512_2048_res": lambda: conv1x1_case(8, 512, 65, 129, 2048, True),
+    "dsn_ce_train": dsn_case,
+    "cs_augment": augment_case,
     "abn_stats_stem": lambda: abn_case(8, 64, 256, 512, "stats"),
     "abn_apply_stem": lambda: abn_case(8, 64, 256, 512, "apply"),
     "abn_bwd_stem": lambda: abn_case(8, 64, 256, 512, "bwd"),
